@@ -1,0 +1,139 @@
+"""Deterministic synthetic weights / inputs shared by the oracle, the golden generator and the tests.
+
+Test infrastructure.  numpy PCG64 streams keyed by (seed, crc32(name)) so a tensor does not depend on
+construction order, torch version or device.  The distributions follow SURVEY.md 7.2: BatchNorm
+statistics are randomised so BN folding is exercised, conv weights are variance-preserving so
+activations stay O(1) through ~30 layers, and the last 1x1 of the heatmap head is sharpened so
+heatmaps span (0,1) and argmaxes are well separated.
+"""
+import os
+import zlib
+import numpy as np
+
+from .arch import state_dict_spec, person_anchors
+
+
+# logit scales measured by oracle/calibrate.py: tag -> (weight key, bias key)
+_SCALED = {
+    "channel_attention": ("channel_attention.fc.2.weight", "channel_attention.fc.2.bias"),
+    "heatmap_head.channel_attention": ("heatmap_head.channel_attention.fc.2.weight",
+                                       "heatmap_head.channel_attention.fc.2.bias"),
+    "heatmap_head.spatial_attention": ("heatmap_head.spatial_attention.conv.weight",
+                                       "heatmap_head.spatial_attention.conv.bias"),
+    "heatmap_head.final_layer.3": ("heatmap_head.final_layer.3.weight", None),
+}
+
+
+def _rng(seed, name):
+    return np.random.default_rng([int(seed), zlib.crc32(name.encode())])
+
+
+_CALIB_CACHE = None
+
+
+def _calibration():
+    global _CALIB_CACHE
+    if _CALIB_CACHE is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "calibration.npz")
+        with np.load(path) as z:
+            _CALIB_CACHE = {k: z[k] for k in z.files}
+    return _CALIB_CACHE
+
+
+def synth_state_dict(seed=0, in_channels=1, calibrated=True, as_torch=True):
+    """All 318 entries of the reference state_dict, as float32 (int64 for num_batches_tracked).
+
+    calibrated=True applies the committed table of oracle/calibration.npz (see oracle/calibrate.py):
+    BN running stats = measured (de-tuned) input statistics, attention / heat-map logit scales.  The table
+    was derived for seed 0 / in_channels 1; other seeds fall back to the uncalibrated distributions.
+    """
+    spec = state_dict_spec(in_channels=in_channels)
+    cal = _calibration() if (calibrated and seed == 0 and in_channels == 1) else {}
+    out = {}
+    for key, (shape, kind) in spec.items():
+        g = _rng(seed, key)
+        if kind == "conv":
+            fan_in = int(np.prod(shape[1:]))
+            gain = 1.0 if ".fc1." in key or ".fc2." in key or "lateral" in key else np.sqrt(2.0)
+            a = g.standard_normal(shape) * (gain / np.sqrt(fan_in))
+        elif kind == "linear":
+            a = g.standard_normal(shape) * (1.0 / np.sqrt(shape[1]))
+        elif kind == "bias":
+            a = g.standard_normal(shape) * 0.1
+            if key == "heatmap_head.final_layer.3.bias":
+                a = a * 5.0 - 6.0
+        elif kind == "bn_weight":
+            a = g.uniform(0.5, 1.5, shape)
+        elif kind == "bn_bias":
+            a = g.standard_normal(shape) * 0.1
+        elif kind == "bn_mean":
+            a = g.standard_normal(shape) * 0.1
+            ck = "mean:" + key[:-len(".running_mean")]
+            if ck in cal:       # measured (and de-tuned) during calibration
+                a = cal[ck]
+        elif kind == "bn_var":
+            a = g.uniform(0.5, 1.5, shape)
+            ck = "var:" + key[:-len(".running_var")]
+            if ck in cal:
+                a = cal[ck]
+        elif kind == "nbt":
+            out[key] = np.asarray(0, dtype=np.int64)
+            continue
+        elif kind == "anchors":
+            out[key] = person_anchors()
+            continue
+        else:
+            raise KeyError(kind)
+        out[key] = np.ascontiguousarray(a, dtype=np.float32)
+    for tag, (wk, bk) in _SCALED.items():
+        if "scale:" + tag in cal:
+            sc = np.float32(cal["scale:" + tag][0])
+            out[wk] = out[wk] * sc
+            if bk is not None:
+                out[bk] = out[bk] * sc
+    if as_torch:
+        import torch
+        return {k: torch.from_numpy(np.array(v)) for k, v in out.items()}
+    return out
+
+
+def synth_images(batch, in_channels=1, size=224, seed=1234):
+    """randn images, the range `Normalize(0.5, 0.5)` produces (dll/data/transforms.py:32)."""
+    g = _rng(seed, f"images{batch}x{in_channels}x{size}")
+    return g.standard_normal((batch, in_channels, size, size)).astype(np.float32)
+
+
+def synth_boxes(batch, persons, seed=99, zero_slots=()):
+    """Normalised (cx,cy,w,h) boxes; `zero_slots` = iterable of (b,p) set to all-zero (padding)."""
+    g = _rng(seed, f"boxes{batch}x{persons}")
+    cx = g.uniform(0.25, 0.75, (batch, persons))
+    cy = g.uniform(0.25, 0.75, (batch, persons))
+    w = g.uniform(0.2, 0.7, (batch, persons))
+    h = g.uniform(0.2, 0.7, (batch, persons))
+    b = np.stack([cx, cy, w, h], axis=-1).astype(np.float32)
+    for (i, j) in zero_slots:
+        b[i, j] = 0.0
+    return b
+
+
+def synth_blob_heatmaps(n, k=17, h=64, w=48, seed=7, sigma=2.0, noise=0.01):
+    """Gaussian-blob heatmaps for the decode microbench."""
+    g = _rng(seed, f"blobs{n}x{k}x{h}x{w}")
+    cx = g.uniform(0, w - 1, (n, k, 1, 1))
+    cy = g.uniform(0, h - 1, (n, k, 1, 1))
+    amp = g.uniform(0.2, 1.0, (n, k, 1, 1))
+    ys = np.arange(h, dtype=np.float64).reshape(1, 1, h, 1)
+    xs = np.arange(w, dtype=np.float64).reshape(1, 1, 1, w)
+    hm = amp * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / (2 * sigma * sigma))
+    hm = hm + noise * g.uniform(0, 1, (n, k, h, w))
+    return hm.astype(np.float32)
+
+
+def synth_nms_candidates(images, m=100, seed=5):
+    """Seeded NMS candidates: centres U(0,1), sizes U(0.05,0.35), scores U(0,1)."""
+    g = _rng(seed, f"nms{images}x{m}")
+    c = g.uniform(0, 1, (images, m, 2))
+    s = g.uniform(0.05, 0.35, (images, m, 2))
+    boxes = np.concatenate([c, s], axis=-1).astype(np.float32)
+    scores = g.uniform(0, 1, (images, m)).astype(np.float32)
+    return boxes, scores
