@@ -1,0 +1,306 @@
+// MobileNetV3-Small body (torchvision features[0:13]) and FPN laterals, NHWC fp32.
+//   reference: dll/models/backbone.py:247-264 (MobileNetV3Wrapper), :29-37 (LightweightFPN laterals + top-down),
+//              tv:models/mobilenetv3.py:53-116 (InvertedResidual), tv:ops/misc.py:225-261 (SqueezeExcitation)
+// Kernels: stem 3x3/s2 direct conv, register-tiled SIMT GEMM for every 1x1 conv (expand / project / f12 /
+// laterals, with SE-scale on the A operand and residual / nearest-upsample add in the epilogue), depthwise
+// kxk with fused SE squeeze (per-CTA reduction + one atomicAdd per channel), SE excitation MLP.
+#include "kpd_common.cuh"
+
+namespace kpd {
+
+// ------------------------------------------------------------------------------------------------
+// stem: conv3x3 s2 p1 (Cin -> 16) + folded BN + hardswish.  in NCHW fp32, out NHWC fp32.
+// 4 threads per output pixel, each 4 output channels -> one coalesced float4 store per thread.
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, float* __restrict__ out,
+                                                   int B, int Cin, int S) {
+    __shared__ float ws[27 * 16];
+    __shared__ float bs[16];
+    for (int i = threadIdx.x; i < 9 * Cin * 16; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < 16) bs[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int Ho = S / 2;
+    const int64_t total = (int64_t)B * Ho * Ho * 4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int q = (int)(t & 3);
+        const int64_t pix = t >> 2;
+        const int ox = (int)(pix % Ho), oy = (int)((pix / Ho) % Ho), b = (int)(pix / ((int64_t)Ho * Ho));
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = 0; c < Cin; c++) {
+            const float* ip = in + ((int64_t)b * Cin + c) * S * S;
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+                const int iy = oy * 2 - 1 + ky;
+                if (iy < 0 || iy >= S) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                    const int ix = ox * 2 - 1 + kx;
+                    if (ix < 0 || ix >= S) continue;
+                    const float v = __ldg(ip + (int64_t)iy * S + ix);
+                    const float* wp = ws + ((ky * 3 + kx) * Cin + c) * 16 + q * 4;
+                    a0 = fmaf(v, wp[0], a0); a1 = fmaf(v, wp[1], a1); a2 = fmaf(v, wp[2], a2); a3 = fmaf(v, wp[3], a3);
+                }
+            }
+        }
+        float4 r;
+        r.x = apply_act(a0 + bs[q * 4 + 0], ACT_HSWISH); r.y = apply_act(a1 + bs[q * 4 + 1], ACT_HSWISH);
+        r.z = apply_act(a2 + bs[q * 4 + 2], ACT_HSWISH); r.w = apply_act(a3 + bs[q * 4 + 3], ACT_HSWISH);
+        reinterpret_cast<float4*>(out)[t] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pointwise (1x1) convolution as a SIMT GEMM:  out[p][n] = act( sum_k in[p][k]*se[b(p)][k] * w[k][n] + bias[n] ) (+res)
+// Block tile 128 pixels x 64 couts, K chunk 16, 256 threads, thread tile 8x4.
+struct PwArgs {
+    const float* in; const float* w; const float* bias; float* out;
+    int64_t pixels; int cin, cout, act;
+    const float* se_scale; int hw;                 // optional per-(image,k) scale on the input
+    const float* res; int res_mode;                // 0 none, 1 same-shape add, 2 nearest-upsampled add
+    int H, W, up;                                  // res_mode 2: output map H x W, coarse map (H/up) x (W/up)
+    int out_nchw;                                  // 1: write out as [B][cout][hw] (API outputs), hw = H*W
+};
+
+__global__ void __launch_bounds__(256) pw_gemm_kernel(PwArgs a) {
+    __shared__ float xs[16][128 + 4];
+    __shared__ float wsm[16][64 + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;                 // tx -> 4 couts, ty -> 8 pixels
+    const int64_t p0 = (int64_t)blockIdx.x * 128;
+    const int n0 = blockIdx.y * 64;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < a.cin; k0 += 16) {
+        // A tile: 128 pixels x 16 k  (each thread loads 8 elements; k fastest for coalescing over NHWC rows)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int e = tid + i * 256;
+            const int kk = e & 15, pp = e >> 4;
+            const int64_t p = p0 + pp; const int k = k0 + kk;
+            float v = 0.f;
+            if (p < a.pixels && k < a.cin) {
+                v = __ldg(a.in + p * a.cin + k);
+                if (a.se_scale) v *= __ldg(a.se_scale + (p / a.hw) * a.cin + k);
+            }
+            xs[kk][pp] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = tid + i * 256;
+            const int nn = e & 63, kk = e >> 6;
+            const int k = k0 + kk, n = n0 + nn;
+            wsm[kk][nn] = (k < a.cin && n < a.cout) ? __ldg(a.w + (int64_t)k * a.cout + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float xv[8], wv[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) xv[i] = xs[kk][ty * 8 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) wv[j] = wsm[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(xv[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int64_t p = p0 + ty * 8 + i;
+        if (p >= a.pixels) continue;
+        int64_t rbase = 0;
+        if (a.res_mode == 1) rbase = p * a.cout;
+        else if (a.res_mode == 2) {
+            const int x = (int)(p % a.W), y = (int)((p / a.W) % a.H); const int64_t b = p / ((int64_t)a.W * a.H);
+            const int Wc = a.W / a.up, Hc = a.H / a.up;
+            rbase = ((b * Hc + y / a.up) * Wc + x / a.up) * a.cout;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= a.cout) continue;
+            float v = acc[i][j] + (a.bias ? __ldg(a.bias + n) : 0.f);
+            v = apply_act(v, a.act);
+            if (a.res_mode) v += __ldg(a.res + rbase + n);
+            if (a.out_nchw) { const int64_t b = p / a.hw, q = p % a.hw; a.out[(b * a.cout + n) * a.hw + q] = v; }
+            else a.out[p * a.cout + n] = v;
+        }
+    }
+}
+
+static int launch_pw(const PwArgs& a, cudaStream_t s) {
+    dim3 grid((unsigned)((a.pixels + 127) / 128), (unsigned)((a.cout + 63) / 64));
+    pw_gemm_kernel<<<grid, 256, 0, s>>>(a);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+int pointwise(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
+              int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s) {
+    PwArgs a{}; a.in = in; a.w = w; a.bias = bias; a.out = out; a.pixels = pixels; a.cin = cin; a.cout = cout; a.act = act;
+    a.se_scale = se_scale; a.hw = hw_per_image > 0 ? hw_per_image : 1; a.res = residual; a.res_mode = residual ? 1 : 0;
+    return launch_pw(a, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise k x k (stride 1|2, pad (k-1)/2) + folded BN + act, NHWC; optional SE squeeze (sum over H*W per (b,c)).
+// thread = (output pixel, 4 channels).  blockDim = (C/4 rounded to a divisor layout) handled by flat indexing.
+template <int K>
+__global__ void __launch_bounds__(256) dw_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                 const float* __restrict__ bias, float* __restrict__ out,
+                                                 float* __restrict__ pool, int B, int H, int C, int stride, int act) {
+    const int Ho = H / stride, C4 = C >> 2, pad = (K - 1) / 2;
+    const int64_t per_img = (int64_t)Ho * Ho * C4;
+    const int b = blockIdx.y;
+    extern __shared__ float red[];                       // [C] per-block SE partial sums
+    if (pool) { for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f; __syncthreads(); }
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(t % C4); const int64_t pix = t / C4;
+        const int ox = (int)(pix % Ho), oy = (int)(pix / Ho);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < K; ky++) {
+            const int iy = oy * stride - pad + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < K; kx++) {
+                const int ix = ox * stride - pad + kx;
+                if (ix < 0 || ix >= H) continue;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(in + (((int64_t)b * H + iy) * H + ix) * C) + c4);
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (ky * K + kx) * C) + c4);
+                acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+                acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+            }
+        }
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+        float4 r;
+        r.x = apply_act(acc.x + bb.x, act); r.y = apply_act(acc.y + bb.y, act);
+        r.z = apply_act(acc.z + bb.z, act); r.w = apply_act(acc.w + bb.w, act);
+        reinterpret_cast<float4*>(out + (((int64_t)b * Ho + oy) * Ho + ox) * C)[c4] = r;
+        if (pool) {
+            atomicAdd(&red[c4 * 4 + 0], r.x); atomicAdd(&red[c4 * 4 + 1], r.y);
+            atomicAdd(&red[c4 * 4 + 2], r.z); atomicAdd(&red[c4 * 4 + 3], r.w);
+        }
+    }
+    if (pool) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(pool + (int64_t)b * C + i, red[i]);
+    }
+}
+
+// SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 ).  one block per image.
+__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
+                                                    const float* __restrict__ b1, const float* __restrict__ w2,
+                                                    const float* __restrict__ b2, float* __restrict__ scale,
+                                                    int C, int SQ, float inv_hw) {
+    __shared__ float m[576];
+    __shared__ float hid[144];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) m[i] = pool[(int64_t)b * C + i] * inv_hw;
+    __syncthreads();
+    for (int j = threadIdx.x; j < SQ; j += blockDim.x) {
+        float a = b1[j];
+        for (int c = 0; c < C; c++) a = fmaf(m[c], __ldg(w1 + (int64_t)c * SQ + j), a);
+        hid[j] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = b2[c];
+        for (int j = 0; j < SQ; j++) a = fmaf(hid[j], __ldg(w2 + (int64_t)j * C + c), a);
+        scale[(int64_t)b * C + c] = apply_act(a, ACT_HSIGMOID);
+    }
+}
+
+static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, cudaStream_t s) {
+    const int Ho = H / m.stride;
+    const int64_t per_img = (int64_t)Ho * Ho * (m.exp / 4);
+    int gx = (int)std::min<int64_t>((per_img + 255) / 256, 64);
+    dim3 grid(gx, B);
+    const size_t sm = pool ? sizeof(float) * m.exp : 0;
+    if (m.k == 3) dw_kernel<3><<<grid, 256, sm, s>>>(in, m.w_dw, m.b_dw, out, pool, B, H, m.exp, m.stride, m.act);
+    else          dw_kernel<5><<<grid, 256, sm, s>>>(in, m.w_dw, m.b_dw, out, pool, B, H, m.exp, m.stride, m.act);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    ProfScope ps("body", s);
+    char* scratch = ws + L.scratch;
+    const ScratchMap sm = scratch_map(B, S, 1);
+    float* feat[4]; for (int i = 0; i < 4; i++) feat[i] = reinterpret_cast<float*>(ws + L.feat[i]);
+    float* expand = reinterpret_cast<float*>(scratch + sm.expand);
+    float* dwout = reinterpret_cast<float*>(scratch + sm.dwout);
+    float* ping = reinterpret_cast<float*>(scratch + sm.ping);
+    float* pong = reinterpret_cast<float*>(scratch + sm.pong);
+    float* se_pool = reinterpret_cast<float*>(scratch + sm.se_pool);
+    float* se_scale = reinterpret_cast<float*>(scratch + sm.se_scale);
+
+    {
+        const int64_t total = (int64_t)B * (S / 2) * (S / 2) * 4;
+        int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], B, p->in_channels, S);
+        KPD_LAUNCH_CHECK();
+    }
+    const float* cur = feat[0];
+    int H = S / 2;
+    for (int i = 0; i < 11; i++) {
+        const MBBlock& m = p->blocks[i];
+        const int Ho = H / m.stride;
+        const float* x = cur;
+        if (m.w_exp) {
+            KPD_TRY(pointwise(cur, m.w_exp, m.b_exp, expand, (int64_t)B * H * H, m.cin, m.exp, m.act, nullptr, nullptr, 0, s));
+            x = expand;
+        }
+        float* pool = nullptr;
+        if (m.se) { KPD_CUDA(cudaMemsetAsync(se_pool, 0, sizeof(float) * B * m.exp, s)); pool = se_pool; }
+        KPD_TRY(launch_dw(m, x, dwout, pool, B, H, s));
+        const float* scale = nullptr;
+        if (m.se) {
+            se_fc_kernel<<<B, 256, 0, s>>>(se_pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, se_scale, m.exp, m.sq, 1.f / (float)(Ho * Ho));
+            KPD_LAUNCH_CHECK();
+            scale = se_scale;
+        }
+        // block outputs that the FPN consumes are written straight into their feat slot (features.3 / features.8)
+        float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
+        KPD_TRY(pointwise(dwout, m.w_proj, m.b_proj, dst, (int64_t)B * Ho * Ho, m.exp, m.cout, ACT_NONE,
+                          m.res ? cur : nullptr, scale, Ho * Ho, s));
+        cur = dst; H = Ho;
+    }
+    KPD_TRY(pointwise(cur, p->w_last, p->b_last, feat[3], (int64_t)B * H * H, 96, 576, ACT_HSWISH, nullptr, nullptr, 0, s));
+    return 0;
+}
+
+// FPN laterals + top-down pathway (backbone.py:33-37): lat3 = L3(f3); lat2 = L2(f2)+up2(lat3); lat1 = L1(f1)+up2(lat2);
+// lateral0 = L0(f0) + up4(lat1)  -> written to the workspace as the input of fpn_convs[0].
+int run_fpn_laterals(const kpd_plan* p, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    ProfScope ps("fpn_laterals", s);
+    const ScratchMap sm = scratch_map(B, S, 1);
+    char* scratch = ws + L.scratch;
+    float* lat[4] = {reinterpret_cast<float*>(ws + L.lateral0), reinterpret_cast<float*>(scratch + sm.lat1),
+                     reinterpret_cast<float*>(scratch + sm.lat2), reinterpret_cast<float*>(scratch + sm.lat3)};
+    const int hs[4] = {S / 2, S / 8, S / 16, S / 32};
+    const int cin[4] = {16, 24, 48, 576};
+    for (int i = 3; i >= 0; i--) {
+        PwArgs a{}; a.in = reinterpret_cast<const float*>(ws + L.feat[i]); a.w = p->w_lat[i]; a.bias = nullptr; a.out = lat[i];
+        a.pixels = (int64_t)B * hs[i] * hs[i]; a.cin = cin[i]; a.cout = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
+        if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
+        KPD_TRY(launch_pw(a, s));
+    }
+    return 0;
+}
+
+// standalone access for the person heads / final 1x1 (NHWC in; NHWC or NCHW out)
+int pointwise_ex(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
+                 int act, int hw, int out_nchw, cudaStream_t s) {
+    PwArgs a{}; a.in = in; a.w = w; a.bias = bias; a.out = out; a.pixels = pixels; a.cin = cin; a.cout = cout; a.act = act;
+    a.hw = hw > 0 ? hw : 1; a.out_nchw = out_nchw;
+    return launch_pw(a, s);
+}
+
+}  // namespace kpd

@@ -1,0 +1,112 @@
+// Shared declarations of the kpd_b200 library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/kpd_b200.h"
+
+namespace kpd {
+
+// ---------------------------------------------------------------- error handling
+void set_error(const char* fmt, ...);
+extern thread_local int64_t g_launches;
+void prof_begin(const char* tag, cudaStream_t s);
+void prof_end(cudaStream_t s);
+
+#define KPD_CHECK_ARG(cond, ...)                                  \
+    do { if (!(cond)) { kpd::set_error(__VA_ARGS__); return KPD_ERR_ARG; } } while (0)
+#define KPD_CUDA(expr)                                            \
+    do { cudaError_t _e = (expr); if (_e != cudaSuccess) {        \
+        kpd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+        return (int)_e; } } while (0)
+#define KPD_LAUNCH_CHECK()                                        \
+    do { kpd::g_launches++; cudaError_t _e = cudaPeekAtLastError(); if (_e != cudaSuccess) { \
+        kpd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+        return (int)_e; } } while (0)
+#define KPD_TRY(expr) do { int _r = (expr); if (_r != 0) return _r; } while (0)
+
+struct ProfScope {
+    cudaStream_t s;
+    ProfScope(const char* tag, cudaStream_t st) : s(st) { prof_begin(tag, s); }
+    ~ProfScope() { prof_end(s); }
+};
+
+// ---------------------------------------------------------------- activations
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_HSWISH = 2, ACT_HSIGMOID = 3, ACT_SIGMOID = 4 };
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    switch (act) {
+        case ACT_RELU:     return fmaxf(x, 0.f);
+        case ACT_HSWISH:   return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case ACT_HSIGMOID: return fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        case ACT_SIGMOID:  return 1.f / (1.f + expf(-x));
+        default:           return x;
+    }
+}
+
+// ---------------------------------------------------------------- packed model
+struct MBBlock {
+    int cin, k, exp, cout, se, act, stride, res, sq;
+    // device pointers (fp32). pointwise weights are [Cin][Cout] (K-major rows, cout contiguous)
+    const float *w_exp, *b_exp;     // expand 1x1 (+folded BN)        [cin][exp], [exp]   (null if exp==cin)
+    const float *w_dw, *b_dw;       // depthwise kxk (+folded BN)     [k*k][exp], [exp]
+    const float *w_fc1, *b_fc1;     // SE fc1                          [exp][sq], [sq]
+    const float *w_fc2, *b_fc2;     // SE fc2                          [sq][exp], [exp]
+    const float *w_proj, *b_proj;   // project 1x1 (+folded BN)       [exp][cout], [cout]
+};
+
+struct DenseConv {          // 3x3 (or 1x1) dense conv, BN folded
+    int cin, cout, taps;
+    const float* w_simt;            // fp32 [taps][cin][cout]
+    const float* w_tf32;            // fp32 [cout][taps*cin]   (K-major, UMMA B operand)
+    const __nv_bfloat16* w_bf16;    // bf16 [cout][taps*cin]
+    const float* bias;              // fp32 [cout]
+};
+
+}  // namespace kpd
+
+struct kpd_plan {
+    int device;
+    int in_channels, num_keypoints;
+    int sm_count;
+    void* d_blob;           // one allocation holding every packed weight
+    size_t blob_bytes;
+    // body
+    const float *w_stem, *b_stem;                 // [3*3*cin][16], [16]
+    kpd::MBBlock blocks[11];
+    const float *w_last, *b_last;                 // f12 [96][576], [576]
+    // fpn
+    const float* w_lat[4];                        // [cin_i][128]
+    kpd::DenseConv fpn_conv[4];
+    // channel attention (model level): fc0 [8][128]+[8], fc2 [128][8]+[128]
+    const float *ca_w0, *ca_b0, *ca_w2, *ca_b2;
+    // heatmap head
+    const float *hca_w0, *hca_b0, *hca_w2, *hca_b2;   // [4][64],[4],[64][4],[64]
+    const float *sa_w, *sa_b;                          // [2][7][7], [1]
+    kpd::DenseConv head_conv[3];                       // 64->256, 256->256, 256->64
+    const float *w_final, *b_final;                    // [64][17], [17]
+    // person heads
+    const float *w_box[4], *b_box[4], *w_cls[4], *b_cls[4];   // [128][36],[36],[128][9],[9]
+};
+
+namespace kpd {
+constexpr int POOL_PARTS = 64;   // per-image partial blocks of the FPN-0 avg/max pool
+constexpr int ROI_PARTS = 28;    // per-ROI partial blocks of the head channel-attention pool (2 rows each)
+struct ScratchMap { size_t expand, dwout, ping, pong, se_pool, se_scale, lat1, lat2, lat3, pool_part, roi_part, total; };
+ScratchMap scratch_map(int B, int S, int n_rois);
+
+// ---- launchers implemented across the .cu files (all enqueue on `s`, return 0 / cudaError) ----
+int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_fpn_laterals(const kpd_plan* p, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* scratch, cudaStream_t s);
+int run_scores_topk(const kpd_plan* p, int B, const float* avg, const float* mx, float* scores, int32_t* topk, cudaStream_t s);
+int conv_dense_simt(const DenseConv& c, const float* in, float* out, int N, int H, int W, int act,
+                    const int32_t* n_valid, cudaStream_t s);
+int conv_dense_umma(const kpd_plan* p, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
+                    int N, int H, int W, int act, const int32_t* n_valid, cudaStream_t s);
+int pointwise(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
+              int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s);
+}  // namespace kpd

@@ -1,0 +1,321 @@
+// Dense 3x3 / 1x1 convolution as an implicit GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//   reference ops replaced: dll/models/backbone.py:39 fpn_convs[0] (conv3x3 128->128 + BN + ReLU),
+//   dll/models/heatmap_head.py:49-68,31-39 (conv3x3 64->256, 256->256, 256->64, each + bias + BN + ReLU).
+//
+// GEMM view: D[M=128 pixels][N=Cout] += A[M][K] * B[N][K]^T with K = taps*Cin.
+//   * A is never materialised: for every tap the [128 pixels x BK channels] operand tile is ONE 4-D TMA box
+//     {BK ch, tw, th, tn} of the NHWC input, shifted by the tap offset; out-of-image coordinates are zero-filled
+//     by TMA, which implements the padding.  The box lands in shared memory as 128 rows of 128 bytes with the
+//     128-byte swizzle, i.e. exactly the canonical K-major UMMA operand layout.
+//   * B (BN-folded weights, [Cout][taps*Cin] K-major) is a 2-D TMA box {BK, Cout}.
+//   * one elected thread issues tcgen05.mma (M=128, N=Cout, K=32 bytes per instruction), accumulators live in TMEM
+//     (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1), tcgen05.commit releases
+//     shared-memory stages / publishes accumulators through mbarriers.
+//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc),
+//     warps 2-5 epilogue (tcgen05.ld -> +bias -> ReLU -> bf16/fp32 NHWC stores).
+#include "kpd_common.cuh"
+#include <cuda.h>
+
+namespace kpd {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > 40000000u) { printf("kpd: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (BF16) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) addr>>4, [16,30) LBO>>4 (=1, unused for swizzled K-major), [32,46) SBO>>4 (8 rows x 128 B = 1024 B),
+// [46,48) version = 1 (Blackwell), [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct ConvParams {
+    int N, H, W, Cin, Cout, taps;      // N = allocated instances (tensor-map extent)
+    int tw, th, tn;                    // pixel box of one 128-row tile: tw*th*tn == 128
+    int tiles_w, tiles_h, tiles_n;
+    int act, out_bf16, stages;
+    const float* bias;
+    void* out;                         // NHWC [N,H,W,Cout], bf16 or fp32
+    const int32_t* n_valid;            // optional device count of live instances (<= N)
+};
+
+constexpr int UMMA_THREADS = 192;
+constexpr int A_BYTES = 128 * 128;     // 128 rows x 128 bytes
+
+template <bool BF16>
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages x (A | B)] | barriers | tmem slot | bias
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int B_BYTES = p.Cout * 128;
+    const int STAGE_BYTES = A_BYTES + B_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.stages;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
+
+    int tmem_cols = 32; while (tmem_cols < 2 * p.Cout) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_live = p.n_valid ? min(*p.n_valid, p.N) : p.N;
+    const int tiles_n_live = (n_live + p.tn - 1) / p.tn;
+    const int total_tiles = tiles_n_live * p.tiles_h * p.tiles_w;
+    constexpr int BK = BF16 ? 64 : 32;                 // elements per 128-byte K slab
+    const int cchunks = p.Cin / BK;
+    const int kiters = p.taps * cchunks;
+    const int ksz = p.taps == 9 ? 3 : 1, pad = p.taps == 9 ? 1 : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {                                // ---------------- TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
+                const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+                for (int kk = 0; kk < kiters; kk++) {
+                    const int tap = kk / cchunks, cc = kk - tap * cchunks;
+                    const int dy = tap / ksz - pad, dx = tap % ksz - pad;
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_expect_tx(full_bar(stage), (uint32_t)STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    tma_load_4d(sa, &tmA, full_bar(stage), cc * BK, w0 + dx, h0 + dy, n0);
+                    tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), tap * p.Cin + cc * BK, 0);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                // ---------------- MMA issuer
+            // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) (1 = bf16, 2 = tf32), K-major both,
+            // N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t fmt = BF16 ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+                for (int kk = 0; kk < kiters; kk++) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++)      // 4 x 32-byte K steps inside the 128-byte swizzle row
+                        tc_mma<BF16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
+                    tc_commit(empty_bar(stage));        // frees this smem stage once the MMAs above retire
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar(acc));              // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {                                            // ---------------- epilogue warps 2..5
+        const int lg = warp & 3;                        // TMEM lane group this warp may access
+        const int row = lg * 32 + lane;
+        const int rw = row % p.tw, rh = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
+            const int w = iw * p.tw + rw, h = ih * p.th + rh, n = in * p.tn + rn;
+            const bool valid = (w < p.W) && (h < p.H) && (n < n_live);
+            const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.Cout);
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                uint32_t r[32];
+                tc_ld32(taddr + c0, r);
+                tc_wait_ld();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        float x = __uint_as_float(r[j]) + sbias[c0 + j];
+                        v[j] = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
+                    }
+                    if (p.out_bf16) {
+                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            uint4 u;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                            u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+                            u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+                            o[q] = u;
+                        }
+                    } else {
+                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
+                    int N, int H, int W, int act, const int32_t* n_valid, cudaStream_t s) {
+    if (N <= 0) return 0;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
+    const int elt = prec_bf16 ? 2 : 4;
+    const int BK = 128 / elt;
+    if (c.cin % BK != 0 || c.cout % 16 != 0 || c.cout > 256 || c.cout < 16) { set_error("conv_dense_umma: unsupported channels %d->%d", c.cin, c.cout); return KPD_ERR_UNSUPPORTED; }
+    ConvParams p{};
+    p.N = N; p.H = H; p.W = W; p.Cin = c.cin; p.Cout = c.cout; p.taps = c.taps;
+    if (W % 16 == 0 && H % 8 == 0) { p.tw = 16; p.th = 8; p.tn = 1; } else { p.tw = 8; p.th = 8; p.tn = 2; }
+    p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
+    p.act = act; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
+    const int stage_bytes = A_BYTES + c.cout * 128;
+    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64;
+    int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
+    if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + misc;
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)c.cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)c.cin * elt, (cuuint64_t)W * c.cin * elt, (cuuint64_t)H * W * c.cin * elt};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return KPD_ERR_STATE; }
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)c.taps * c.cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)c.cout};
+        cuuint64_t strides[1] = {K * elt};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)c.cout};
+        cuuint32_t es[2] = {1, 1};
+        const void* wptr = prec_bf16 ? static_cast<const void*>(c.w_bf16) : static_cast<const void*>(c.w_tf32);
+        CUresult r = enc(&tmB, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<void*>(wptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return KPD_ERR_STATE; }
+    }
+    const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int grid = std::min(total_tiles, plan->sm_count);
+    if (prec_bf16) {
+        KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_umma_kernel<true><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);
+    } else {
+        KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_umma_kernel<false><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);
+    }
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace kpd

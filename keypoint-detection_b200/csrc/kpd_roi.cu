@@ -1,0 +1,235 @@
+// ROI stage: box compaction, batched legacy ROI-align over the 64 selected FPN-0 channels, and the heat-map head's
+// CBAM attention, all without the reference's per-box Python loop.
+//   reference: dll/models/keypoint_model.py:137-170 (loop, zero-box skip), :212-228 (extract_roi_features),
+//              :630-638 (box_center_to_corners), tv:ops/roi_align.py (aligned=False, sampling_ratio=-1),
+//              dll/models/heatmap_head.py:94-101,115-151 (ChannelAttention, SpatialAttention)
+#include "kpd_common.cuh"
+
+namespace kpd {
+
+// ------------------------------------------------------------------------------------------------
+// Order-preserving compaction of the non-zero boxes.  One block; thread b scans image b's P boxes.
+__global__ void __launch_bounds__(1024) build_rois_kernel(const float* __restrict__ boxes, int B, int P,
+                                                          float* __restrict__ roi_box, int32_t* __restrict__ roi_batch,
+                                                          int32_t* __restrict__ roi_slot, int32_t* __restrict__ img_count,
+                                                          int32_t* __restrict__ roi_count) {
+    extern __shared__ int32_t cnt[];       // [B] counts -> exclusive offsets
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int c = 0;
+        for (int p = 0; p < P; p++) {
+            const float4 v = reinterpret_cast<const float4*>(boxes)[(int64_t)b * P + p];
+            c += !(v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f);
+        }
+        cnt[b] = c; img_count[b] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 0; b < B; b++) { const int c = cnt[b]; cnt[b] = run; run += c; }
+        *roi_count = run;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int n = cnt[b], rank = 0;
+        for (int p = 0; p < P; p++) {
+            const float4 v = reinterpret_cast<const float4*>(boxes)[(int64_t)b * P + p];
+            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+            reinterpret_cast<float4*>(roi_box)[n] = v;
+            roi_batch[n] = b; roi_slot[n] = b * P + rank;
+            n++; rank++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROI-align (legacy, adaptive sampling) of channels topk[b][0..63] of fpn0 [B,H,W,128] -> roi_feat [N,56,56,64] fp32.
+// grid (ROI_PARTS, Nmax): each block handles 2 output rows; a warp handles one output pixel at a time with
+// lanes over channels (2 per lane) so the gather of one bilinear tap touches the 4 cache lines of one NHWC pixel.
+// Also emits per-block partial sum/max per channel for the head's channel attention.
+__global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict__ fpn0, const int32_t* __restrict__ topk,
+                                                        const float* __restrict__ roi_box, const int32_t* __restrict__ roi_batch,
+                                                        const int32_t* __restrict__ roi_count, float* __restrict__ roi_feat,
+                                                        float* __restrict__ part, int H, int W) {
+    const int n = blockIdx.y;
+    if (n >= *roi_count) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = roi_batch[n];
+    const float4 bx = reinterpret_cast<const float4*>(roi_box)[n];
+    // box_center_to_corners + scaling to feature pixels (keypoint_model.py:224-226, :630-638)
+    const float x1 = fminf(fmaxf(bx.x - bx.z / 2.f, 0.f), 1.f) * (float)W;
+    const float y1 = fminf(fmaxf(bx.y - bx.w / 2.f, 0.f), 1.f) * (float)H;
+    const float x2 = fminf(fmaxf(bx.x + bx.z / 2.f, 0.f), 1.f) * (float)W;
+    const float y2 = fminf(fmaxf(bx.y + bx.w / 2.f, 0.f), 1.f) * (float)H;
+    const float rw = fmaxf(x2 - x1, 1.f), rh = fmaxf(y2 - y1, 1.f);
+    const float bin_h = rh / 56.f, bin_w = rw / 56.f;
+    const int gh = (int)ceilf(rh / 56.f), gw = (int)ceilf(rw / 56.f);
+    const float count = (float)max(gh * gw, 1);
+    const int c0 = topk[b * KPD_TOPK + lane], c1 = topk[b * KPD_TOPK + lane + 32];
+    const float* fb = fpn0 + (int64_t)b * H * W * 128;
+    float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
+    const int row0 = blockIdx.x * 2;
+    for (int q = warp; q < 2 * 56; q += 8) {
+        const int ph = row0 + q / 56, pw = q % 56;
+        float a0 = 0.f, a1 = 0.f;
+        for (int iy = 0; iy < gh; iy++) {
+            float y = y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh;
+            const bool yok = !(y < -1.f || y > (float)H);
+            y = fmaxf(y, 0.f);
+            int yl = (int)y, yh;
+            if (yl >= H - 1) { yl = yh = H - 1; y = (float)yl; } else yh = yl + 1;
+            const float ly = y - (float)yl, hy = 1.f - ly;
+            for (int ix = 0; ix < gw; ix++) {
+                float x = x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw;
+                const bool ok = yok && !(x < -1.f || x > (float)W);
+                x = fmaxf(x, 0.f);
+                int xl = (int)x, xh;
+                if (xl >= W - 1) { xl = xh = W - 1; x = (float)xl; } else xh = xl + 1;
+                const float lx = x - (float)xl, hx = 1.f - lx;
+                if (!ok) continue;
+                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                const float* p1 = fb + ((int64_t)yl * W + xl) * 128; const float* p2 = fb + ((int64_t)yl * W + xh) * 128;
+                const float* p3 = fb + ((int64_t)yh * W + xl) * 128; const float* p4 = fb + ((int64_t)yh * W + xh) * 128;
+                a0 += w1 * __ldg(p1 + c0) + w2 * __ldg(p2 + c0) + w3 * __ldg(p3 + c0) + w4 * __ldg(p4 + c0);
+                a1 += w1 * __ldg(p1 + c1) + w2 * __ldg(p2 + c1) + w3 * __ldg(p3 + c1) + w4 * __ldg(p4 + c1);
+            }
+        }
+        a0 /= count; a1 /= count;
+        float* o = roi_feat + (((int64_t)n * 56 + ph) * 56 + pw) * 64;
+        o[lane] = a0; o[lane + 32] = a1;
+        s0 += a0; s1 += a1; m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1);
+    }
+    __shared__ float ss[8][64], sm[8][64];
+    ss[warp][lane] = s0; ss[warp][lane + 32] = s1; sm[warp][lane] = m0; sm[warp][lane + 32] = m1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f, m = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { s += ss[i][threadIdx.x]; m = fmaxf(m, sm[i][threadIdx.x]); }
+        float* o = part + (((int64_t)n * ROI_PARTS + blockIdx.x) * 2) * 64;
+        o[threadIdx.x] = s; o[64 + threadIdx.x] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head attention (one block per ROI): cw = sigmoid(MLP(avg)+MLP(max)); x*=cw; sw = sigmoid(conv7x7([mean_c,max_c])+b);
+// x*=sw; write the input of deconv_layers[0] as fp32 or bf16 NHWC.
+template <typename OutT>
+__global__ void __launch_bounds__(256) head_attention_kernel(const float* __restrict__ roi_feat, const float* __restrict__ part,
+                                                             const int32_t* __restrict__ roi_count,
+                                                             const float* __restrict__ w0, const float* __restrict__ b0,
+                                                             const float* __restrict__ w2, const float* __restrict__ b2,
+                                                             const float* __restrict__ saw, const float* __restrict__ sab,
+                                                             float* __restrict__ out_cw, float* __restrict__ out_sw,
+                                                             OutT* __restrict__ out) {
+    const int n = blockIdx.x;
+    if (n >= *roi_count) return;
+    constexpr int HW = 56 * 56;
+    extern __shared__ float smem[];
+    float* mean_map = smem;              // [56*56]
+    float* max_map = smem + HW;          // [56*56]
+    float* sw = smem + 2 * HW;           // [56*56]
+    __shared__ float avg[64], mx[64], cw[64], hid[8], wk[98];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) {
+        float s = 0.f, m = -INFINITY;
+        for (int i = 0; i < ROI_PARTS; i++) {
+            const float* o = part + (((int64_t)n * ROI_PARTS + i) * 2) * 64;
+            s += o[tid]; m = fmaxf(m, o[64 + tid]);
+        }
+        avg[tid] = s / (float)HW; mx[tid] = m;
+    }
+    if (tid < 98) wk[tid] = saw[tid];
+    __syncthreads();
+    if (tid < 8) {       // hidden units: 0..3 avg branch, 4..7 max branch
+        const int j = tid & 3; const float* v = tid < 4 ? avg : mx;
+        float a = b0[j];
+        for (int k = 0; k < 64; k++) a = fmaf(v[k], w0[j * 64 + k], a);
+        hid[tid] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float oa = b2[tid], om = b2[tid];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { oa = fmaf(hid[j], w2[tid * 4 + j], oa); om = fmaf(hid[4 + j], w2[tid * 4 + j], om); }
+        const float c = 1.f / (1.f + expf(-(oa + om)));
+        cw[tid] = c; out_cw[(int64_t)n * 64 + tid] = c;
+    }
+    __syncthreads();
+    const float* x = roi_feat + (int64_t)n * HW * 64;
+    const float cw0 = cw[lane], cw1 = cw[lane + 32];
+    for (int p = warp; p < HW; p += 8) {
+        const float v0 = x[(int64_t)p * 64 + lane] * cw0, v1 = x[(int64_t)p * 64 + lane + 32] * cw1;
+        float s = v0 + v1, m = fmaxf(v0, v1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+        if (lane == 0) { mean_map[p] = s / 64.f; max_map[p] = m; }
+    }
+    __syncthreads();
+    const float bias = sab[0];
+    for (int p = tid; p < HW; p += 256) {
+        const int y = p / 56, xx = p % 56;
+        float a = bias;
+        for (int ky = 0; ky < 7; ky++) {
+            const int iy = y + ky - 3;
+            if (iy < 0 || iy >= 56) continue;
+            for (int kx = 0; kx < 7; kx++) {
+                const int ix = xx + kx - 3;
+                if (ix < 0 || ix >= 56) continue;
+                a = fmaf(mean_map[iy * 56 + ix], wk[ky * 7 + kx], a);
+                a = fmaf(max_map[iy * 56 + ix], wk[49 + ky * 7 + kx], a);
+            }
+        }
+        const float sv = 1.f / (1.f + expf(-a));
+        sw[p] = sv; out_sw[(int64_t)n * HW + p] = sv;
+    }
+    __syncthreads();
+    OutT* o = out + (int64_t)n * HW * 64;
+    for (int64_t e = tid; e < (int64_t)HW * 64; e += 256) {
+        const int c = (int)(e & 63); const int p = (int)(e >> 6);
+        const float v = (x[e] * cw[c]) * sw[p];
+        if constexpr (sizeof(OutT) == 2) o[e] = __float2bfloat16_rn(v); else o[e] = v;
+    }
+}
+
+int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    build_rois_kernel<<<1, 1024, sizeof(int32_t) * B, s>>>(boxes, B, P, reinterpret_cast<float*>(ws + L.roi_box),
+        reinterpret_cast<int32_t*>(ws + L.roi_batch), reinterpret_cast<int32_t*>(ws + L.roi_slot),
+        reinterpret_cast<int32_t*>(ws + L.img_count), reinterpret_cast<int32_t*>(ws + L.roi_count));
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    ProfScope ps("roi_align", s);
+    const ScratchMap sm = scratch_map(B, S, n_max + 1);
+    roi_align_kernel<<<dim3(ROI_PARTS, n_max), 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.fpn0), topk,
+        reinterpret_cast<const float*>(ws + L.roi_box), reinterpret_cast<const int32_t*>(ws + L.roi_batch),
+        reinterpret_cast<const int32_t*>(ws + L.roi_count), reinterpret_cast<float*>(ws + L.roi_feat),
+        reinterpret_cast<float*>(ws + L.scratch + sm.roi_part), S / 2, S / 2);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    ProfScope ps("head_attention", s);
+    const ScratchMap sm = scratch_map(B, S, n_max + 1);
+    const size_t dyn = sizeof(float) * 3 * 56 * 56;
+    const float* part = reinterpret_cast<const float*>(ws + L.scratch + sm.roi_part);
+    if (out_bf16) {
+        KPD_CUDA(cudaFuncSetAttribute(head_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        head_attention_kernel<__nv_bfloat16><<<n_max, 256, dyn, s>>>(reinterpret_cast<const float*>(ws + L.roi_feat), part,
+            reinterpret_cast<const int32_t*>(ws + L.roi_count), p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, p->sa_w, p->sa_b,
+            reinterpret_cast<float*>(ws + L.head_cw), reinterpret_cast<float*>(ws + L.head_sw),
+            reinterpret_cast<__nv_bfloat16*>(ws + L.head_in));
+    } else {
+        KPD_CUDA(cudaFuncSetAttribute(head_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        head_attention_kernel<float><<<n_max, 256, dyn, s>>>(reinterpret_cast<const float*>(ws + L.roi_feat), part,
+            reinterpret_cast<const int32_t*>(ws + L.roi_count), p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, p->sa_w, p->sa_b,
+            reinterpret_cast<float*>(ws + L.head_cw), reinterpret_cast<float*>(ws + L.head_sw),
+            reinterpret_cast<float*>(ws + L.head_in));
+    }
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace kpd

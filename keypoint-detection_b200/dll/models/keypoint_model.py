@@ -1,0 +1,196 @@
+"""Multi-person keypoint model: drop-in for the reference's dll/models/keypoint_model.py inference path.
+
+Same constructor, attribute tree (=> same 318 state_dict keys), batch-dict contract and output layout as the
+reference's MultiPersonKeypointModel (keypoint_model.py:46-210); the whole forward + heat-map decode runs as
+hand-written sm_100a kernels behind the C-ABI of libkpd_b200.so (one call per forward, no per-box Python loop,
+no host synchronisation).  Training (loss, backward) is outside the hot path and not provided.
+"""
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from ..configs.model_config import ModelConfig
+from ..configs.training_config import TrainingConfig
+from ._runtime import PlanCache, Workspace, as_cuda_f32, stage_views
+from ._spec import ParamTree, channel_attention_entries
+from .backbone import MobileNetV3Wrapper
+from .heatmap_head import HeatmapHead, decode_model_heatmap
+from .person_head import PERSON_HEAD
+
+
+class ChannelAttention(ParamTree):
+    """Parameter container for keypoint_model.py:18-44 (Linear(C, C/16) + ReLU + Linear(C/16, C), both pools)."""
+
+    def __init__(self, in_channels, reduction_ratio=16):
+        super().__init__(channel_attention_entries(in_channels, reduction_ratio))
+        self.in_channels = in_channels
+
+
+class _InferenceOnlyLoss(nn.Module):
+    """Placeholder for `loss_fn` (keypoint_model.py:65-69): parameter-free, so state_dict is unaffected."""
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training loss is outside the B200 inference hot path")
+
+
+class MultiPersonKeypointModel(nn.Module):
+    """Multi-person keypoint detection model (inference): backbone -> channel top-k -> ROI-align -> heat-map head -> decode."""
+
+    def __init__(self, config: ModelConfig, training_config: TrainingConfig = None, precision: str = "fp32"):
+        super().__init__()
+        self.config = config
+        self.training_config = training_config
+        self.backbone = MobileNetV3Wrapper(config.backbone)
+        self.person_detector = PERSON_HEAD(config.person_head)
+        self.heatmap_head = HeatmapHead(config.heatmap_head)
+        self.channel_attention = ChannelAttention(in_channels=config.backbone.out_channels, reduction_ratio=16)
+        self.loss_fn = _InferenceOnlyLoss()
+        self.num_keypoints = config.num_keypoints
+        if config.backbone.out_channels != 128 or config.num_keypoints != 17 or config.heatmap_head.in_channels != 64:
+            raise ValueError("the B200 hot path is built for out_channels=128, num_keypoints=17, heatmap_head.in_channels=64")
+        self.set_precision(precision)
+        self._plans = PlanCache(config.backbone.in_channels, config.num_keypoints)
+        self._workspace = Workspace()
+        self._tensors = None
+        self._last = None
+
+    # ------------------------------------------------------------------ plumbing
+    def set_precision(self, precision: str):
+        """'fp32' (tcgen05 tf32, fp32 storage), 'bf16' (bf16 head, tf32 trunk) or 'fp32_strict' (CUDA-core debug)."""
+        if precision not in N.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(N.PRECISIONS)}")
+        self.precision = precision
+        return self
+
+    def _apply(self, fn, *a, **k):
+        self._tensors = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._tensors = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _plan(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise N.NativeLibraryError("model parameters are on %s: move the model to a CUDA device (no CPU fallback)" % dev)
+        if self._tensors is None:
+            self._tensors = dict(self.state_dict(keep_vars=True))
+        return self._plans.get(self._tensors, dev), dev
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, batch, topk_override=None):
+        """Same contract as keypoint_model.py:73-210 (inference).  batch: dict with 'image' [B,C,S,S] and 'bboxes'
+        ([Tensor[B,P,4]] | [Tensor[P,4]] | Tensor[B,P,4]; normalised cx,cy,w,h; all-zero rows = padding)."""
+        x = batch['image'] if isinstance(batch, dict) else batch
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("Input must be a tensor or a dict with 'image' key containing a tensor")
+        if self.training:
+            raise RuntimeError("inference-only drop-in: call model.eval() (or model.predict(batch))")
+        if x.dim() != 4 or x.size(1) != self.config.backbone.in_channels or x.size(2) != x.size(3) or x.size(2) % 32:
+            raise ValueError(f"image must be [B,{self.config.backbone.in_channels},S,S] with S % 32 == 0, got {tuple(x.shape)}")
+        plan, dev = self._plan()
+        batch_size = x.size(0)
+
+        if isinstance(batch, dict) and 'bboxes' in batch:
+            pb = batch['bboxes']
+            if isinstance(pb, list) and len(pb) > 0:
+                t = pb[0]
+                if t.dim() == 3:
+                    boxes = t
+                elif t.dim() == 2:
+                    boxes = t.unsqueeze(0)
+                else:
+                    raise ValueError(f"Invalid bboxes tensor format: {t.shape}")
+            elif isinstance(pb, torch.Tensor):
+                if pb.dim() == 3 and pb.size(-1) == 4:
+                    boxes = pb
+                else:
+                    raise ValueError(f"Invalid bboxes format: {pb.shape}")
+            else:
+                boxes = torch.zeros(batch_size, 0, 4, device=dev)
+        else:
+            # upstream routes this case to PERSON_HEAD.forward, which fails with a channel mismatch
+            # (SURVEY.md 0.5); there is no reference behaviour to reproduce.
+            raise NotImplementedError("forward() needs batch['bboxes']: the person-detector path has no reference semantics")
+        if boxes.size(-1) != 4:
+            raise ValueError(f"Invalid bboxes format: {boxes.shape}")
+        person_bboxes = [boxes[i] for i in range(boxes.size(0))]
+        K = self.num_keypoints
+        if boxes.size(0) == 0 or boxes.size(1) == 0:
+            # keypoint_model.py:121-135 -- eval-mode empty result (note the reference's differing ranks)
+            return {'keypoints': torch.zeros(batch_size, 1, K, 2, device=dev),
+                    'visibilities': torch.zeros(batch_size, 1, K, device=dev),
+                    'heatmap': torch.zeros(batch_size, 1, K, 56, 56, device=dev),
+                    'boxes': person_bboxes if person_bboxes else [torch.zeros(0, 4, device=dev) for _ in range(batch_size)]}
+        if boxes.size(0) != batch_size:
+            raise ValueError(f"bboxes batch {boxes.size(0)} != image batch {batch_size}")
+
+        with torch.cuda.device(dev):
+            x = as_cuda_f32(x, dev)
+            bx = as_cuda_f32(boxes, dev)
+            P, S = bx.size(1), x.size(2)
+            prec = N.PRECISIONS[self.precision]
+            L = plan.layout(batch_size, S, batch_size * P, prec)
+            ws = self._workspace.get(L.total_bytes, dev)
+            heat = torch.empty(batch_size, P, K, 56, 56, device=dev, dtype=torch.float32)
+            kpts = torch.empty(batch_size, P, 1, K, 2, device=dev, dtype=torch.float32)
+            vis = torch.empty(batch_size, P, 1, K, 3, device=dev, dtype=torch.float32)
+            tk = None
+            if topk_override is not None:
+                tk = topk_override.to(device=dev, dtype=torch.int32).contiguous()
+            N.check(N.load().kpd_forward(plan.handle, prec, N.ptr(x), batch_size, S, N.ptr(bx), P, N.ptr(tk),
+                                         N.ptr(heat), N.ptr(kpts), N.ptr(vis), N.ptr(ws), L.total_bytes,
+                                         N.stream_ptr(dev)), "kpd_forward")
+            self._last = (ws, L, batch_size, S, batch_size * P, prec)
+        return {'heatmap': heat, 'keypoints': kpts, 'visibilities': vis, 'boxes': person_bboxes}
+
+    @torch.no_grad()
+    def predict(self, batch, **kw):
+        """eval() + no_grad forward (BASELINE north star: the reference itself has no predict method)."""
+        self.eval()
+        return self.forward(batch, **kw)
+
+    def stage_tensors(self):
+        """Views (NHWC) of the intermediate tensors of the last forward, for stage-wise parity tests."""
+        if self._last is None:
+            raise RuntimeError("no forward has run yet")
+        return stage_views(*self._last)
+
+    # ------------------------------------------------------------------ reference helper methods
+    def decode_heatmap(self, heatmap, threshold=0.1):
+        """keypoint_model.py:250-282: soft-argmax keypoints [B,K,2] + one-hot 3-class visibilities [B,K,3]."""
+        return decode_model_heatmap(heatmap)
+
+    def convert_to_original_coords(self, keypoints, box):
+        """keypoint_model.py:230-248 (host glue; the fused forward does this inside the decode kernel)."""
+        shape = keypoints.shape
+        k = keypoints.reshape(-1, 2)
+        cx, cy, w, h = box
+        xs = torch.clamp(k[:, 0] * w + (cx - w / 2), 0, 1)
+        ys = torch.clamp(k[:, 1] * h + (cy - h / 2), 0, 1)
+        return torch.stack([xs, ys], dim=-1).view(shape)
+
+    def extract_roi_features(self, features: torch.Tensor, box: torch.Tensor, output_size: Tuple[int, int] = (56, 56)):
+        raise NotImplementedError("ROI-align runs fused inside forward(); the standalone method is not part of the hot path")
+
+
+def box_center_to_corners(box):
+    """keypoint_model.py:630-638."""
+    cx, cy, w, h = box.unbind()
+    return torch.stack([torch.clamp(cx - w / 2, 0, 1), torch.clamp(cy - h / 2, 0, 1),
+                        torch.clamp(cx + w / 2, 0, 1), torch.clamp(cy + h / 2, 0, 1)])
+
+
+def pad_to_length(tensor_list, length):
+    """keypoint_model.py:640-651."""
+    if len(tensor_list) == 0:
+        return []
+    if len(tensor_list) >= length:
+        return tensor_list[:length]
+    return tensor_list + [torch.zeros_like(tensor_list[0]) for _ in range(length - len(tensor_list))]
