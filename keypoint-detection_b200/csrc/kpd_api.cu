@@ -15,7 +15,7 @@ int run_decode(const DecodeArgs& a, int dtype, int sm_count, cudaStream_t s);
 int run_dummy_person(const int32_t* img_count, float* vis, int B, int P, int K, cudaStream_t s);
 int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int pointwise_ex(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
                  int act, int hw, int out_nchw, cudaStream_t s);
 
@@ -61,11 +61,12 @@ __global__ void __launch_bounds__(128) head_final_kernel(const T* __restrict__ i
     for (int k = 0; k < 17; k++) o[(int64_t)k * HW] = 1.f / (1.f + expf(-acc[k]));
 }
 
+// round_out: the fp32 result feeds another kind::tf32 MMA -> store it rounded-to-nearest tf32
 static int dense_conv(const kpd_plan* p, const DenseConv& c, int precision, int use_bf16, const void* in, void* out,
-                      int N, int H, int W, const int32_t* n_valid, cudaStream_t s) {
+                      int N, int H, int W, int round_out, const int32_t* n_valid, cudaStream_t s) {
     if (precision == KPD_PREC_FP32_SIMT)
         return conv_dense_simt(c, static_cast<const float*>(in), static_cast<float*>(out), N, H, W, ACT_RELU, n_valid, s);
-    return conv_dense_umma(p, c, use_bf16, in, out, use_bf16, N, H, W, ACT_RELU, n_valid, s);
+    return conv_dense_umma(p, c, use_bf16, in, out, use_bf16, N, H, W, ACT_RELU, (round_out && !use_bf16) ? 1 : 0, n_valid, s);
 }
 
 static int check_layout(const kpd_plan* plan, const void* ws, const kpd_workspace_layout* L) {
@@ -104,18 +105,18 @@ static int run_head_stack(const kpd_plan* plan, int precision, int B_for_scratch
                           const kpd_workspace_layout& L, float* d_heatmap, cudaStream_t s) {
     const int use_bf16 = precision == KPD_PREC_BF16;
     const int32_t* n_valid = reinterpret_cast<const int32_t*>(ws + L.roi_count);
-    KPD_TRY(run_head_attention(plan, B_for_scratch, S, n_max, use_bf16, ws, L, s));
+    KPD_TRY(run_head_attention(plan, B_for_scratch, S, n_max, use_bf16, precision == KPD_PREC_TF32, ws, L, s));
     {
         ProfScope ps("head_conv1", s);
-        KPD_TRY(dense_conv(plan, plan->head_conv[0], precision, use_bf16, ws + L.head_in, ws + L.head_a, n_max, 56, 56, n_valid, s));
+        KPD_TRY(dense_conv(plan, plan->head_conv[0], precision, use_bf16, ws + L.head_in, ws + L.head_a, n_max, 56, 56, 1, n_valid, s));
     }
     {
         ProfScope ps("head_conv2", s);
-        KPD_TRY(dense_conv(plan, plan->head_conv[1], precision, use_bf16, ws + L.head_a, ws + L.head_b, n_max, 56, 56, n_valid, s));
+        KPD_TRY(dense_conv(plan, plan->head_conv[1], precision, use_bf16, ws + L.head_a, ws + L.head_b, n_max, 56, 56, 1, n_valid, s));
     }
     {
         ProfScope ps("head_conv3", s);
-        KPD_TRY(dense_conv(plan, plan->head_conv[2], precision, use_bf16, ws + L.head_b, ws + L.head_c, n_max, 56, 56, n_valid, s));
+        KPD_TRY(dense_conv(plan, plan->head_conv[2], precision, use_bf16, ws + L.head_b, ws + L.head_c, n_max, 56, 56, 0, n_valid, s));
     }
     {
         ProfScope ps("head_final", s);
@@ -142,10 +143,10 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     KPD_TRY(run_body(plan, d_images, B, S, ws, L, s));
-    KPD_TRY(run_fpn_laterals(plan, B, S, ws, L, s));
+    KPD_TRY(run_fpn_laterals(plan, B, S, precision != KPD_PREC_FP32_SIMT, ws, L, s));
     {
         ProfScope ps("fpn0_conv", s);
-        KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, S / 2, S / 2, nullptr, s));
+        KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, S / 2, S / 2, 0, nullptr, s));
     }
     const ScratchMap sm = scratch_map(B, S, 1);
     KPD_TRY(run_pools(reinterpret_cast<const float*>(ws + L.fpn0), B, (S / 2) * (S / 2), reinterpret_cast<float*>(ws + L.pool_avg),

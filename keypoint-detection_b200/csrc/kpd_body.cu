@@ -5,8 +5,11 @@
 // laterals, with SE-scale on the A operand and residual / nearest-upsample add in the epilogue), depthwise
 // kxk with fused SE squeeze (per-CTA reduction + one atomicAdd per channel), SE excitation MLP.
 #include "kpd_common.cuh"
+#include <stdlib.h>
 
 namespace kpd {
+
+int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out, int B, int H, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // stem: conv3x3 s2 p1 (Cin -> 16) + folded BN + hardswish.  in NCHW fp32, out NHWC fp32.
@@ -59,6 +62,7 @@ struct PwArgs {
     const float* res; int res_mode;                // 0 none, 1 same-shape add, 2 nearest-upsampled add
     int H, W, up;                                  // res_mode 2: output map H x W, coarse map (H/up) x (W/up)
     int out_nchw;                                  // 1: write out as [B][cout][hw] (API outputs), hw = H*W
+    int round_tf32;                                // 1: round the result to tf32 (it feeds a kind::tf32 MMA)
 };
 
 __global__ void __launch_bounds__(256) pw_gemm_kernel(PwArgs a) {
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(PwArgs a) {
             float v = acc[i][j] + (a.bias ? __ldg(a.bias + n) : 0.f);
             v = apply_act(v, a.act);
             if (a.res_mode) v += __ldg(a.res + rbase + n);
+            if (a.round_tf32) v = tf32_rna(v);
             if (a.out_nchw) { const int64_t b = p / a.hw, q = p % a.hw; a.out[(b * a.cout + n) * a.hw + q] = v; }
             else a.out[p * a.cout + n] = v;
         }
@@ -249,9 +254,16 @@ int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, con
     }
     const float* cur = feat[0];
     int H = S / 2;
+    static const bool unfused = getenv("KPD_BODY_UNFUSED") != nullptr;     // debugging aid: layer-by-layer kernels
     for (int i = 0; i < 11; i++) {
         const MBBlock& m = p->blocks[i];
         const int Ho = H / m.stride;
+        if (!unfused) {
+            float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
+            const int r = run_mbconv(p, m, cur, dst, B, H, s);
+            if (r == 0) { cur = dst; H = Ho; continue; }
+            if (r != KPD_ERR_UNSUPPORTED) return r;                         // does not fit on chip (large S): layer-by-layer
+        }
         const float* x = cur;
         if (m.w_exp) {
             KPD_TRY(pointwise(cur, m.w_exp, m.b_exp, expand, (int64_t)B * H * H, m.cin, m.exp, m.act, nullptr, nullptr, 0, s));
@@ -276,9 +288,55 @@ int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, con
     return 0;
 }
 
+// lateral_convs[0] (1x1, 16 -> 128, no bias) + nearest x`up` upsample-add of the coarser lateral: a pure streaming
+// kernel (64 B in, 512 B out per pixel).  One warp per pixel strip; lane l owns output channels 4l..4l+3 and keeps its
+// 16x4 weight slice in registers; the 16 input channels of a pixel are a warp-uniform (broadcast) 64-byte load.
+__global__ void __launch_bounds__(256) lateral0_kernel(const float* __restrict__ feat0, const float* __restrict__ w,
+                                                       const float* __restrict__ coarse, float* __restrict__ out,
+                                                       int64_t pixels, int H, int W, int up, int round_tf32) {
+    __shared__ float4 ws4[16][32];
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) ws4[i >> 5][i & 31] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    __syncthreads();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int Wc = W / up, Hc = H / up;
+    constexpr int PX = 4;                                  // pixels in flight per warp iteration
+    for (int64_t p0 = warp * PX; p0 < pixels; p0 += nwarps * PX) {
+        float4 xv[PX][4], acc[PX];
+#pragma unroll
+        for (int j = 0; j < PX; j++) {
+            const int64_t p = min(p0 + j, pixels - 1);
+            const float4* ip = reinterpret_cast<const float4*>(feat0 + p * 16);
+            xv[j][0] = __ldg(ip); xv[j][1] = __ldg(ip + 1); xv[j][2] = __ldg(ip + 2); xv[j][3] = __ldg(ip + 3);
+            const int x = (int)(p % W), y = (int)((p / W) % H); const int64_t b = p / ((int64_t)W * H);
+            acc[j] = __ldg(reinterpret_cast<const float4*>(coarse + ((b * Hc + y / up) * Wc + x / up) * 128) + lane);
+        }
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+            const float4 w0 = ws4[k4 * 4 + 0][lane], w1 = ws4[k4 * 4 + 1][lane], w2 = ws4[k4 * 4 + 2][lane], w3 = ws4[k4 * 4 + 3][lane];
+#pragma unroll
+            for (int j = 0; j < PX; j++) {
+                const float4 xx = xv[j][k4];
+                acc[j].x = fmaf(xx.x, w0.x, acc[j].x); acc[j].y = fmaf(xx.x, w0.y, acc[j].y); acc[j].z = fmaf(xx.x, w0.z, acc[j].z); acc[j].w = fmaf(xx.x, w0.w, acc[j].w);
+                acc[j].x = fmaf(xx.y, w1.x, acc[j].x); acc[j].y = fmaf(xx.y, w1.y, acc[j].y); acc[j].z = fmaf(xx.y, w1.z, acc[j].z); acc[j].w = fmaf(xx.y, w1.w, acc[j].w);
+                acc[j].x = fmaf(xx.z, w2.x, acc[j].x); acc[j].y = fmaf(xx.z, w2.y, acc[j].y); acc[j].z = fmaf(xx.z, w2.z, acc[j].z); acc[j].w = fmaf(xx.z, w2.w, acc[j].w);
+                acc[j].x = fmaf(xx.w, w3.x, acc[j].x); acc[j].y = fmaf(xx.w, w3.y, acc[j].y); acc[j].z = fmaf(xx.w, w3.z, acc[j].z); acc[j].w = fmaf(xx.w, w3.w, acc[j].w);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PX; j++) {
+            if (p0 + j >= pixels) break;
+            float4 a = acc[j];
+            if (round_tf32) { a.x = tf32_rna(a.x); a.y = tf32_rna(a.y); a.z = tf32_rna(a.z); a.w = tf32_rna(a.w); }
+            reinterpret_cast<float4*>(out + (p0 + j) * 128)[lane] = a;
+        }
+    }
+}
+
 // FPN laterals + top-down pathway (backbone.py:33-37): lat3 = L3(f3); lat2 = L2(f2)+up2(lat3); lat1 = L1(f1)+up2(lat2);
 // lateral0 = L0(f0) + up4(lat1)  -> written to the workspace as the input of fpn_convs[0].
-int run_fpn_laterals(const kpd_plan* p, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     ProfScope ps("fpn_laterals", s);
     const ScratchMap sm = scratch_map(B, S, 1);
     char* scratch = ws + L.scratch;
@@ -287,9 +345,18 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, char* ws, const kpd_worksp
     const int hs[4] = {S / 2, S / 8, S / 16, S / 32};
     const int cin[4] = {16, 24, 48, 576};
     for (int i = 3; i >= 0; i--) {
+        if (i == 0) {
+            const int64_t pixels = (int64_t)B * hs[0] * hs[0];
+            const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)p->sm_count * 8);
+            lateral0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0],
+                                                 pixels, hs[0], hs[0], hs[0] / hs[1], round_tf32);
+            KPD_LAUNCH_CHECK();
+            break;
+        }
         PwArgs a{}; a.in = reinterpret_cast<const float*>(ws + L.feat[i]); a.w = p->w_lat[i]; a.bias = nullptr; a.out = lat[i];
         a.pixels = (int64_t)B * hs[i] * hs[i]; a.cin = cin[i]; a.cout = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
+        a.round_tf32 = (i == 0) ? round_tf32 : 0;
         KPD_TRY(launch_pw(a, s));
     }
     return 0;

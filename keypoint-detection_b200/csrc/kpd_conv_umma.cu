@@ -88,7 +88,7 @@ struct ConvParams {
     int N, H, W, Cin, Cout, taps;      // N = allocated instances (tensor-map extent)
     int tw, th, tn;                    // pixel box of one 128-row tile: tw*th*tn == 128
     int tiles_w, tiles_h, tiles_n;
-    int act, out_bf16, stages;
+    int act, out_bf16, stages, round_out_tf32;
     const float* bias;
     void* out;                         // NHWC [N,H,W,Cout], bf16 or fp32
     const int32_t* n_valid;            // optional device count of live instances (<= N)
@@ -211,7 +211,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         float x = __uint_as_float(r[j]) + sbias[c0 + j];
-                        v[j] = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
+                        x = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
+                        v[j] = p.round_out_tf32 ? tf32_rna(x) : x;
                     }
                     if (p.out_bf16) {
                         uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
@@ -263,7 +264,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
-                    int N, int H, int W, int act, const int32_t* n_valid, cudaStream_t s) {
+                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s) {
     if (N <= 0) return 0;
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
@@ -274,7 +275,7 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     p.N = N; p.H = H; p.W = W; p.Cin = c.cin; p.Cout = c.cout; p.taps = c.taps;
     if (W % 16 == 0 && H % 8 == 0) { p.tw = 16; p.th = 8; p.tn = 1; } else { p.tw = 8; p.th = 8; p.tn = 2; }
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
-    p.act = act; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
+    p.act = act; p.round_out_tf32 = round_out_tf32; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
     const int stage_bytes = A_BYTES + c.cout * 128;
     const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64;
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;

@@ -95,6 +95,13 @@ static void pack_conv_kc(Blob& B, const float* w, const float* cbias, const BN* 
 }
 
 static __nv_bfloat16 to_bf16(float f) { return __float2bfloat16_rn(f); }
+// fp32 -> tf32 round-to-nearest (ties away), same result as cvt.rna.tf32.f32 for finite values
+static float to_tf32(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
 
 // dense conv for the tensor-core path: [cout][taps*cin] K-major (k index = tap*cin + c), fp32 and bf16 copies
 static void pack_dense(Blob& B, const float* w, const float* cbias, const BN* bn, double eps, int cout, int cin, int k,
@@ -111,7 +118,7 @@ static void pack_dense(Blob& B, const float* w, const float* cbias, const BN* bn
             for (int t = 0; t < taps; t++) {
                 float v = (float)((double)w[((size_t)o * cin + c) * taps + t] * sc[o]);
                 B.f(off[0])[((size_t)t * cin + c) * cout + o] = v;
-                B.f(off[1])[(size_t)o * K + (size_t)t * cin + c] = v;
+                B.f(off[1])[(size_t)o * K + (size_t)t * cin + c] = to_tf32(v);
                 reinterpret_cast<__nv_bfloat16*>(B.h.data() + off[2])[(size_t)o * K + (size_t)t * cin + c] = to_bf16(v);
             }
         B.f(off[3])[o] = (float)((cbias ? (double)cbias[o] * sc[o] : 0.0) + sh[o]);

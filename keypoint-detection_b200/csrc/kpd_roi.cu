@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) head_attention_kernel(const float* __rest
                                                              const float* __restrict__ w2, const float* __restrict__ b2,
                                                              const float* __restrict__ saw, const float* __restrict__ sab,
                                                              float* __restrict__ out_cw, float* __restrict__ out_sw,
-                                                             OutT* __restrict__ out) {
+                                                             OutT* __restrict__ out, int round_tf32) {
     const int n = blockIdx.x;
     if (n >= *roi_count) return;
     constexpr int HW = 56 * 56;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) head_attention_kernel(const float* __rest
     for (int64_t e = tid; e < (int64_t)HW * 64; e += 256) {
         const int c = (int)(e & 63); const int p = (int)(e >> 6);
         const float v = (x[e] * cw[c]) * sw[p];
-        if constexpr (sizeof(OutT) == 2) o[e] = __float2bfloat16_rn(v); else o[e] = v;
+        if constexpr (sizeof(OutT) == 2) o[e] = __float2bfloat16_rn(v); else o[e] = round_tf32 ? tf32_rna(v) : v;
     }
 }
 
@@ -210,7 +210,7 @@ int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const 
     return 0;
 }
 
-int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     ProfScope ps("head_attention", s);
     const ScratchMap sm = scratch_map(B, S, n_max + 1);
     const size_t dyn = sizeof(float) * 3 * 56 * 56;
@@ -220,13 +220,13 @@ int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16,
         head_attention_kernel<__nv_bfloat16><<<n_max, 256, dyn, s>>>(reinterpret_cast<const float*>(ws + L.roi_feat), part,
             reinterpret_cast<const int32_t*>(ws + L.roi_count), p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, p->sa_w, p->sa_b,
             reinterpret_cast<float*>(ws + L.head_cw), reinterpret_cast<float*>(ws + L.head_sw),
-            reinterpret_cast<__nv_bfloat16*>(ws + L.head_in));
+            reinterpret_cast<__nv_bfloat16*>(ws + L.head_in), 0);
     } else {
         KPD_CUDA(cudaFuncSetAttribute(head_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         head_attention_kernel<float><<<n_max, 256, dyn, s>>>(reinterpret_cast<const float*>(ws + L.roi_feat), part,
             reinterpret_cast<const int32_t*>(ws + L.roi_count), p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, p->sa_w, p->sa_b,
             reinterpret_cast<float*>(ws + L.head_cw), reinterpret_cast<float*>(ws + L.head_sw),
-            reinterpret_cast<float*>(ws + L.head_in));
+            reinterpret_cast<float*>(ws + L.head_in), round_tf32);
     }
     KPD_LAUNCH_CHECK();
     return 0;

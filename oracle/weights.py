@@ -40,8 +40,37 @@ def _calibration():
     return _CALIB_CACHE
 
 
-def synth_state_dict(seed=0, in_channels=1, calibrated=True, as_torch=True):
+def _stock_tensor(key, shape, kind, g):
+    """Reference-style random init (what `MultiPersonKeypointModel(...)` holds before training): torchvision /
+    HeatmapHead.init_weights use kaiming_normal(fan_out) + zero bias + identity BN; the dll-defined FPN, person head
+    and attention layers keep PyTorch's default kaiming_uniform(a=sqrt(5)) weights and uniform biases."""
+    fan_out_style = key.startswith("backbone.body.") or key.startswith("heatmap_head.deconv") or \
+        key.startswith("heatmap_head.final") or key.startswith("heatmap_head.spatial")
+    if kind in ("conv", "linear"):
+        fan_in = int(np.prod(shape[1:]))
+        if kind == "conv" and fan_out_style:
+            fan_out = shape[0] * int(np.prod(shape[2:]))
+            return g.standard_normal(shape) * np.sqrt(2.0 / fan_out)
+        bound = 1.0 / np.sqrt(fan_in)            # kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+        return g.uniform(-bound, bound, shape)
+    if kind == "bias":
+        if fan_out_style:
+            return np.zeros(shape)
+        fan = {"channel_attention.fc.0.bias": 128, "channel_attention.fc.2.bias": 8,
+               "heatmap_head.channel_attention.fc.0.bias": 64, "heatmap_head.channel_attention.fc.2.bias": 4}.get(key, 128)
+        return g.uniform(-1.0 / np.sqrt(fan), 1.0 / np.sqrt(fan), shape)
+    if kind in ("bn_weight", "bn_var"):
+        return np.ones(shape)
+    if kind in ("bn_bias", "bn_mean"):
+        return np.zeros(shape)
+    raise KeyError(kind)
+
+
+def synth_state_dict(seed=0, in_channels=1, calibrated=True, as_torch=True, style="calibrated"):
     """All 318 entries of the reference state_dict, as float32 (int64 for num_batches_tracked).
+
+    style="stock": reference-style random initialisation (flat heat maps, near-tied channel scores -- the literal
+    "random-init weights" condition of BASELINE.json); style="calibrated" (default): the stress set described below.
 
     calibrated=True applies the committed table of oracle/calibration.npz (see oracle/calibrate.py):
     BN running stats = measured (de-tuned) input statistics, attention / heat-map logit scales.  The table
@@ -52,6 +81,9 @@ def synth_state_dict(seed=0, in_channels=1, calibrated=True, as_torch=True):
     out = {}
     for key, (shape, kind) in spec.items():
         g = _rng(seed, key)
+        if style == "stock" and kind not in ("nbt", "anchors"):
+            out[key] = np.ascontiguousarray(_stock_tensor(key, shape, kind, _rng(seed + 1000, key)), dtype=np.float32)
+            continue
         if kind == "conv":
             fan_in = int(np.prod(shape[1:]))
             gain = 1.0 if ".fc1." in key or ".fc2." in key or "lateral" in key else np.sqrt(2.0)
@@ -86,7 +118,7 @@ def synth_state_dict(seed=0, in_channels=1, calibrated=True, as_torch=True):
             raise KeyError(kind)
         out[key] = np.ascontiguousarray(a, dtype=np.float32)
     for tag, (wk, bk) in _SCALED.items():
-        if "scale:" + tag in cal:
+        if style != "stock" and "scale:" + tag in cal:
             sc = np.float32(cal["scale:" + tag][0])
             out[wk] = out[wk] * sc
             if bk is not None:

@@ -106,6 +106,27 @@ def run_case(model, name, batch, size, persons, zero_slots):
 
 
 @torch.no_grad()
+def run_stock(model, calibrated_sd):
+    """Reference-style random init ('stock'): flat heat maps and near-tied channel scores."""
+    model.load_state_dict(synth_state_dict(seed=0, style="stock"), strict=True)
+    x = torch.from_numpy(synth_images(2, 1, 224, seed=1234))
+    boxes = torch.from_numpy(synth_boxes(2, 3, seed=99, zero_slots=((0, 1),)))
+    cap = {}
+    h = model.channel_attention.register_forward_hook(lambda m, i, o: cap.setdefault("scores", o))
+    out = model({"image": x, "bboxes": boxes})
+    h.remove()
+    scores = cap["scores"]
+    srt = torch.sort(scores, dim=1, descending=True).values
+    print(f"[stock] heatmap range {float(out['heatmap'][out['heatmap'] > 0].min()):.4f}..{float(out['heatmap'].max()):.4f} "
+          f"min top-65 score gap {float((srt[:, :64] - srt[:, 1:65]).min()):.3e}")
+    np.savez_compressed(os.path.join(HERE, "forward_stock_s224_b2_p3.npz"), scores=scores.numpy(),
+                        topk=torch.topk(scores, 64, dim=1).indices.numpy().astype(np.int64),
+                        heatmap=out["heatmap"].numpy(), keypoints=out["keypoints"].numpy(),
+                        visibilities=out["visibilities"].numpy(), boxes=boxes.numpy())
+    model.load_state_dict(calibrated_sd, strict=True)
+
+
+@torch.no_grad()
 def run_degenerate(model):
     """bboxes=None / every list empty -> the eval-mode 'empty_output' shapes (keypoint_model.py:123-135)."""
     x = torch.from_numpy(synth_images(2, 1, 224, seed=1234))
@@ -188,6 +209,7 @@ def main():
             f.write(f"{k} {list(v.shape)} {str(v.dtype).replace('torch.', '')}\n")
     for name, kw in GOLDEN_CASES.items():
         run_case(model, name, **kw)
+    run_stock(model, synth_state_dict(seed=0))
     run_degenerate(model)
     run_decoders(model)
     run_nms(model)

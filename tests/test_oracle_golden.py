@@ -68,6 +68,17 @@ def test_forward_stages_match_reference(sd, case):
     np.testing.assert_array_equal(hm.argmax(dim=2).numpy(), g["heatmap_argmax"])
 
 
+def test_forward_stock_random_init_matches_reference():
+    g = _load("forward_stock_s224_b2_p3.npz")
+    sd = synth_state_dict(seed=0, style="stock")
+    x = synth_images(2, 1, 224, seed=1234)
+    out = OM.forward(sd, torch.from_numpy(x), torch.from_numpy(g["boxes"]), topk_override=g["topk"], return_stages=True)
+    np.testing.assert_allclose(out["stages"]["scores"].numpy(), g["scores"], atol=2e-7)
+    np.testing.assert_allclose(out["heatmap"].numpy(), g["heatmap"], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(out["keypoints"].numpy(), g["keypoints"], atol=2e-6)
+    np.testing.assert_array_equal(out["visibilities"].numpy(), g["visibilities"])
+
+
 def test_forward_without_boxes_returns_reference_empty_shapes(sd):
     g = _load("forward_no_boxes.npz")
     x = synth_images(2, 1, 224, seed=1234)
