@@ -68,26 +68,40 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeArgs a) {
         const int nvec = HW / VEC;                       // the API guarantees HW % VEC == 0
         const int step = 32 * VEC, dxs = step % a.W, dys = step / a.W;
         int x0 = (lane * VEC) % a.W, y0 = (lane * VEC) / a.W;      // coordinates of element 0 of this lane's vector
-        for (int v0 = lane; v0 < nvec; v0 += 32) {
-            float v[VEC]; Elt<T>::load(h + (int64_t)v0 * VEC, v);
+        constexpr int UN = 4;                            // independent 16-byte loads in flight per lane
+        for (int vb = lane; vb < nvec; vb += 32 * UN) {
+            float v[UN][VEC];
 #pragma unroll
-            for (int j = 0; j < VEC; j++)
-                if (v[j] > best) { best = v[j]; best_i = v0 * VEC + j; }
-            if (want_soft) {
-                float vm = v[0];
+            for (int u = 0; u < UN; u++) {
+                const int v0 = vb + 32 * u;
+                if (v0 < nvec) Elt<T>::load(h + (int64_t)v0 * VEC, v[u]);
+                else {
 #pragma unroll
-                for (int j = 1; j < VEC; j++) vm = fmaxf(vm, v[j]);
-                vm *= a.inv_temp;
-                if (vm > sf.m) { const float r = __expf(sf.m - vm); sf.s *= r; sf.sx *= r; sf.sy *= r; sf.m = vm; }
-#pragma unroll
-                for (int j = 0; j < VEC; j++) {
-                    int xx = x0 + j, yy = y0;
-                    if (xx >= a.W) { xx -= a.W; yy++; }
-                    const float e = __expf(fmaf(v[j], a.inv_temp, -sf.m));
-                    sf.s += e; sf.sx = fmaf(e, (float)xx, sf.sx); sf.sy = fmaf(e, (float)yy, sf.sy);
+                    for (int j = 0; j < VEC; j++) v[u][j] = -INFINITY;
                 }
-                x0 += dxs; y0 += dys;
-                if (x0 >= a.W) { x0 -= a.W; y0++; }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int v0 = vb + 32 * u;
+#pragma unroll
+                for (int j = 0; j < VEC; j++)
+                    if (v[u][j] > best) { best = v[u][j]; best_i = v0 * VEC + j; }
+                if (want_soft && v0 < nvec) {
+                    float vm = v[u][0];
+#pragma unroll
+                    for (int j = 1; j < VEC; j++) vm = fmaxf(vm, v[u][j]);
+                    vm *= a.inv_temp;
+                    if (vm > sf.m) { const float r = __expf(sf.m - vm); sf.s *= r; sf.sx *= r; sf.sy *= r; sf.m = vm; }
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) {
+                        int xx = x0 + j, yy = y0;
+                        if (xx >= a.W) { xx -= a.W; yy++; }
+                        const float e = __expf(fmaf(v[u][j], a.inv_temp, -sf.m));
+                        sf.s += e; sf.sx = fmaf(e, (float)xx, sf.sx); sf.sy = fmaf(e, (float)yy, sf.sy);
+                    }
+                    x0 += dxs; y0 += dys;
+                    if (x0 >= a.W) { x0 -= a.W; y0++; }
+                }
             }
         }
 #pragma unroll
