@@ -32,7 +32,7 @@ FLOP_PER_IMAGE = 9.42e9          # SURVEY.md 8d (S=224, P=1, dead FPN levels ski
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32_strict"])
@@ -92,13 +92,17 @@ class ClockSampler:
 
 
 def make_inputs(batch, size, persons):
-    from oracle.weights import synth_images, synth_boxes
-    x = synth_images(batch, 1, size, seed=1234)
+    """Synthetic batch: randn images (the range Normalize(0.5, 0.5) produces), one full-image box per image for
+    P=1 (the canonical throughput point) or seeded random boxes for P>1."""
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(batch, 1, size, size, generator=g)
     if persons == 1:
-        boxes = np.tile(np.asarray([0.5, 0.5, 1.0, 1.0], dtype=np.float32), (batch, 1, 1))
+        boxes = torch.tensor([0.5, 0.5, 1.0, 1.0]).repeat(batch, 1, 1)
     else:
-        boxes = synth_boxes(batch, persons, seed=99)
-    return torch.from_numpy(x), torch.from_numpy(boxes)
+        c = 0.25 + 0.5 * torch.rand(batch, persons, 2, generator=g)
+        wh = 0.2 + 0.5 * torch.rand(batch, persons, 2, generator=g)
+        boxes = torch.cat([c, wh], dim=-1)
+    return x.contiguous(), boxes.contiguous()
 
 
 def cpu_reference(args, seconds, steps=None, warmup=1):
@@ -147,7 +151,6 @@ def main():
 
     from dll import MultiPersonKeypointModel, _native
     from dll.configs.config_loader import load_config
-    from oracle.weights import synth_state_dict          # seeded random-init weights (no checkpoint exists upstream)
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -156,8 +159,8 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     cfg = load_config(os.path.join(ROOT, "configs", "default_config.yaml"))
+    torch.manual_seed(0)                 # random-init weights of the reference architecture (no checkpoint exists upstream)
     model = MultiPersonKeypointModel(cfg.model, cfg.training, precision=args.precision)
-    model.load_state_dict(synth_state_dict(0), strict=True)
     model = model.to(dev).eval()
     lib = _native.load()
 
@@ -235,11 +238,16 @@ def main():
     conv2_flops = 2.0 * n_roi * 56 * 56 * 256 * 2304
     dom = "head_conv2"
     roof = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")     # dram bytes/launch from the committed ncu capture
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(f"{dom}_{args.precision}_B{B}")
+        traffic = t["dram_bytes_per_launch"] if t else None
     if dom in kern:
         ach = conv2_flops / (kern[dom] * 1e-3) / 1e12
         peak = pk["tensor"] if args.precision == "bf16" else pk["tensor"] / 2
         roof = {"bound": "tensor", "kernel": "conv_umma_kernel (head conv 256->256, 3x3)", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "peak_source": f"{pk['source']} bf16 sustained" + ("" if args.precision == "bf16" else " / 2 (tf32 nominal half rate)"),
                 "flops_per_launch": conv2_flops, "ms_per_launch": kern[dom]}
     line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -253,11 +261,16 @@ def main():
                     "d2h_bytes_per_step": int(kp_host.numel() * 4 + vis_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof,
             "kernels_ms": kern,
+            "roofline_other": {
+                "fpn0_conv (tcgen05 tf32, 3.70 GFLOP/img)": None if "fpn0_conv" not in kern else
+                    {"achieved_tflops": 2.0 * B * (S // 2) ** 2 * 128 * 1152 / (kern["fpn0_conv"] * 1e-3) / 1e12, "peak_tflops": pk["tensor"] / 2},
+                "body (13 fused kernels, fp32 FMA; algorithmic bytes 0.77 M elem x 4 B per image)": None if "body" not in kern else
+                    {"achieved_gbs": B * 0.77e6 * 4 / (kern["body"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]},
+                "decode (fp32 heat maps 17x56x56 per ROI)": None if "decode" not in kern else
+                    {"achieved_gbs": n_roi * (17 * 3136 * 4 + 340) / (kern["decode"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]}},
             "model_tflops": value * FLOP_PER_IMAGE / 1e12 / world}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only (task contract)
         line["cpu_baseline"] = cpu_reference(args, args.cpu_baseline_seconds)
-    elif not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(args, min(args.cpu_baseline_seconds, 6.0))
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
