@@ -142,8 +142,8 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     const kpd_workspace_layout& L = *layout;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
-    KPD_TRY(run_body(plan, d_images, B, S, ws, L, s));
-    KPD_TRY(run_fpn_laterals(plan, B, S, precision != KPD_PREC_FP32_SIMT, ws, L, s));
+    KPD_TRY(run_body(plan, d_images, B, S, precision == KPD_PREC_FP32_SIMT, ws, L, s));
+    KPD_TRY(run_fpn_laterals(plan, B, S, precision != KPD_PREC_FP32_SIMT, precision == KPD_PREC_FP32_SIMT, ws, L, s));
     {
         ProfScope ps("fpn0_conv", s);
         KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, S / 2, S / 2, 0, nullptr, s));

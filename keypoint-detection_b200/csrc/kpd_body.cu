@@ -9,7 +9,18 @@
 
 namespace kpd {
 
-int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out, int B, int H, cudaStream_t s);
+int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out, int B, int H, int strict_fp32, cudaStream_t s);
+
+struct PwMma {
+    const float* A; const float4* Wf; const float* bias; float* out;
+    int64_t M; int K, N, act;
+    const float* se_scale; int hw;
+    const float* res; int res_mode;
+    int H, W, up;
+    int round_tf32;
+};
+int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s);
+int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // stem: conv3x3 s2 p1 (Cin -> 16) + folded BN + hardswish.  in NCHW fp32, out NHWC fp32.
@@ -210,15 +221,23 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ po
     for (int i = threadIdx.x; i < C; i += blockDim.x) m[i] = pool[(int64_t)b * C + i] * inv_hw;
     __syncthreads();
     for (int j = threadIdx.x; j < SQ; j += blockDim.x) {
-        float a = b1[j];
-        for (int c = 0; c < C; c++) a = fmaf(m[c], __ldg(w1 + (int64_t)c * SQ + j), a);
-        hid[j] = fmaxf(a, 0.f);
+        float a0 = b1[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;                 // C % 8 == 0; 8 independent loads in flight
+#pragma unroll 2
+        for (int c = 0; c < C; c += 4) {
+            a0 = fmaf(m[c], __ldg(w1 + (int64_t)c * SQ + j), a0); a1 = fmaf(m[c + 1], __ldg(w1 + (int64_t)(c + 1) * SQ + j), a1);
+            a2 = fmaf(m[c + 2], __ldg(w1 + (int64_t)(c + 2) * SQ + j), a2); a3 = fmaf(m[c + 3], __ldg(w1 + (int64_t)(c + 3) * SQ + j), a3);
+        }
+        hid[j] = fmaxf((a0 + a1) + (a2 + a3), 0.f);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = b2[c];
-        for (int j = 0; j < SQ; j++) a = fmaf(hid[j], __ldg(w2 + (int64_t)j * C + c), a);
-        scale[(int64_t)b * C + c] = apply_act(a, ACT_HSIGMOID);
+        float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;                 // SQ % 8 == 0
+#pragma unroll 2
+        for (int j = 0; j < SQ; j += 4) {
+            a0 = fmaf(hid[j], __ldg(w2 + (int64_t)j * C + c), a0); a1 = fmaf(hid[j + 1], __ldg(w2 + (int64_t)(j + 1) * C + c), a1);
+            a2 = fmaf(hid[j + 2], __ldg(w2 + (int64_t)(j + 2) * C + c), a2); a3 = fmaf(hid[j + 3], __ldg(w2 + (int64_t)(j + 3) * C + c), a3);
+        }
+        scale[(int64_t)b * C + c] = apply_act((a0 + a1) + (a2 + a3), ACT_HSIGMOID);
     }
 }
 
@@ -234,7 +253,57 @@ static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool,
     return 0;
 }
 
-int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+// Batch-wide trunk: every 1x1 conv is one tensor-core GEMM over all B*H*W pixels (3xTF32 mma.sync), every depthwise
+// conv one batch-wide kernel.  At the batch sizes of the benchmark configs the per-image problems (<= 56x56 pixels)
+// are too small to fill an SM, so the batch-wide form beats the one-cluster-per-image fused kernel (kpd_mbconv.cu);
+// the intermediates (expanded / depthwise tensors) stay L2-resident for B*H*W*C*4 B <= ~100 MB.
+static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    char* scratch = ws + L.scratch;
+    const ScratchMap sm = scratch_map(B, S, 1);
+    float* feat[4]; for (int i = 0; i < 4; i++) feat[i] = reinterpret_cast<float*>(ws + L.feat[i]);
+    float* expand = reinterpret_cast<float*>(scratch + sm.expand);
+    float* dwout = reinterpret_cast<float*>(scratch + sm.dwout);
+    float* ping = reinterpret_cast<float*>(scratch + sm.ping);
+    float* pong = reinterpret_cast<float*>(scratch + sm.pong);
+    float* se_pool = reinterpret_cast<float*>(scratch + sm.se_pool);
+    float* se_scale = reinterpret_cast<float*>(scratch + sm.se_scale);
+    {
+        const int64_t total = (int64_t)B * (S / 2) * (S / 2) * 4;
+        int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], B, p->in_channels, S);
+        KPD_LAUNCH_CHECK();
+    }
+    const float* cur = feat[0];
+    int H = S / 2;
+    for (int i = 0; i < 11; i++) {
+        const MBBlock& m = p->blocks[i];
+        const int Ho = H / m.stride;
+        const float* x = cur;
+        if (m.w_exp) {
+            PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act;
+            KPD_TRY(pointwise_mma(a, p->sm_count, s));
+            x = expand;
+        }
+        float* pool = nullptr;
+        if (m.se) { KPD_CUDA(cudaMemsetAsync(se_pool, 0, sizeof(float) * B * m.exp, s)); pool = se_pool; }
+        KPD_TRY(depthwise_batched(m, x, dwout, pool, B, H, p->sm_count, s));
+        if (m.se) {
+            se_fc_kernel<<<B, 256, 0, s>>>(se_pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, se_scale, m.exp, m.sq, 1.f / (float)(Ho * Ho));
+            KPD_LAUNCH_CHECK();
+        }
+        float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
+        PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
+        a.se_scale = m.se ? se_scale : nullptr; a.hw = Ho * Ho; a.res = m.res ? cur : nullptr; a.res_mode = m.res ? 1 : 0;
+        KPD_TRY(pointwise_mma(a, p->sm_count, s));
+        cur = dst; H = Ho;
+    }
+    PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH;
+    return pointwise_mma(a, p->sm_count, s);
+}
+
+int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+    static const bool fused = getenv("KPD_BODY_FUSED") != nullptr;           // one-cluster-per-image fused MBConv kernels
+    if (!strict_fp32 && !fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, ws, L, s); }
     ProfScope ps("body", s);
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
@@ -260,7 +329,7 @@ int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, con
         const int Ho = H / m.stride;
         if (!unfused) {
             float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
-            const int r = run_mbconv(p, m, cur, dst, B, H, s);
+            const int r = run_mbconv(p, m, cur, dst, B, H, strict_fp32, s);
             if (r == 0) { cur = dst; H = Ho; continue; }
             if (r != KPD_ERR_UNSUPPORTED) return r;                         // does not fit on chip (large S): layer-by-layer
         }
@@ -336,7 +405,7 @@ __global__ void __launch_bounds__(256) lateral0_kernel(const float* __restrict__
 
 // FPN laterals + top-down pathway (backbone.py:33-37): lat3 = L3(f3); lat2 = L2(f2)+up2(lat3); lat1 = L1(f1)+up2(lat2);
 // lateral0 = L0(f0) + up4(lat1)  -> written to the workspace as the input of fpn_convs[0].
-int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     ProfScope ps("fpn_laterals", s);
     const ScratchMap sm = scratch_map(B, S, 1);
     char* scratch = ws + L.scratch;
@@ -344,6 +413,20 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, char* ws, 
                      reinterpret_cast<float*>(scratch + sm.lat2), reinterpret_cast<float*>(scratch + sm.lat3)};
     const int hs[4] = {S / 2, S / 8, S / 16, S / 32};
     const int cin[4] = {16, 24, 48, 576};
+    for (int i = 3; i >= 1 && !strict_fp32; i--) {     // tensor-core laterals 3..1 (3xTF32 GEMM + nearest-upsample add)
+        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.out = lat[i];
+        a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
+        if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
+        KPD_TRY(pointwise_mma(a, p->sm_count, s));
+    }
+    if (!strict_fp32) {                                 // lateral 0 (K=16): dedicated streaming kernel (512 B/pixel out)
+        const int64_t pixels = (int64_t)B * hs[0] * hs[0];
+        const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)p->sm_count * 8);
+        lateral0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0],
+                                             pixels, hs[0], hs[0], hs[0] / hs[1], round_tf32);
+        KPD_LAUNCH_CHECK();
+    }
+    if (!strict_fp32) return 0;
     for (int i = 3; i >= 0; i--) {
         if (i == 0) {
             const int64_t pixels = (int64_t)B * hs[0] * hs[0];

@@ -63,6 +63,9 @@ struct MBBlock {
     const float *w_fc1, *b_fc1;     // SE fc1                          [exp][sq], [sq]
     const float *w_fc2, *b_fc2;     // SE fc2                          [sq][exp], [exp]
     const float *w_proj, *b_proj;   // project 1x1 (+folded BN)       [exp][cout], [cout]
+    // the same 1x1 weights pre-split for 3xTF32 mma.sync (m16n8k8 B fragments): float4 [K/8][N/8][32 lanes] =
+    // (b0_hi, b1_hi, b0_lo, b1_lo), b0 = W[k0+t][n0+g], b1 = W[k0+t+4][n0+g], g = lane>>2, t = lane&3
+    const float4 *wf_exp, *wf_proj;
 };
 
 struct DenseConv {          // 3x3 (or 1x1) dense conv, BN folded
@@ -85,8 +88,10 @@ struct kpd_plan {
     const float *w_stem, *b_stem;                 // [3*3*cin][16], [16]
     kpd::MBBlock blocks[11];
     const float *w_last, *b_last;                 // f12 [96][576], [576]
+    const float4* wf_last;                        // f12 as 3xTF32 mma fragments
     // fpn
     const float* w_lat[4];                        // [cin_i][128]
+    const float4* wf_lat[4];                      // laterals as 3xTF32 mma fragments
     kpd::DenseConv fpn_conv[4];
     // channel attention (model level): fc0 [8][128]+[8], fc2 [128][8]+[128]
     const float *ca_w0, *ca_b0, *ca_w2, *ca_b2;
@@ -106,8 +111,8 @@ struct ScratchMap { size_t expand, dwout, ping, pong, se_pool, se_scale, lat1, l
 ScratchMap scratch_map(int B, int S, int n_rois);
 
 // ---- launchers implemented across the .cu files (all enqueue on `s`, return 0 / cudaError) ----
-int run_body(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* scratch, cudaStream_t s);
 int run_scores_topk(const kpd_plan* p, int B, const float* avg, const float* mx, float* scores, int32_t* topk, cudaStream_t s);
 int conv_dense_simt(const DenseConv& c, const float* in, float* out, int N, int H, int W, int act,

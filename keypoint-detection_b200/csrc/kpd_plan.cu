@@ -125,6 +125,23 @@ static void pack_dense(Blob& B, const float* w, const float* cbias, const BN* bn
     }
 }
 
+// 3xTF32 B-fragment packing of a [K][N] matrix already stored in the blob at `off_w` (see MBBlock::wf_exp)
+static size_t pack_mma_frag(Blob& B, size_t off_w, int K, int N) {
+    const int k8 = K / 8, n8 = N / 8;
+    size_t off = B.alloc(sizeof(float) * 4 * (size_t)k8 * n8 * 32);
+    for (int kb = 0; kb < k8; kb++)
+        for (int nb = 0; nb < n8; nb++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, t = lane & 3;
+                const float b0 = B.f(off_w)[(size_t)(kb * 8 + t) * N + nb * 8 + g];
+                const float b1 = B.f(off_w)[(size_t)(kb * 8 + t + 4) * N + nb * 8 + g];
+                const float h0 = to_tf32(b0), h1 = to_tf32(b1);
+                float* d = B.f(off) + (((size_t)kb * n8 + nb) * 32 + lane) * 4;
+                d[0] = h0; d[1] = h1; d[2] = to_tf32(b0 - h0); d[3] = to_tf32(b1 - h1);
+            }
+    return off;
+}
+
 static size_t pack_raw(Blob& B, const float* src, size_t n) {
     size_t off = B.alloc(sizeof(float) * n);
     memcpy(B.f(off), src, sizeof(float) * n);
@@ -205,6 +222,7 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
             const float* w = c.next(); BN bn = read_bn(c);
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.exp, m.cin, 1, ow, ob);
             reg(&m.w_exp, ow); reg(&m.b_exp, ob);
+            reg(&m.wf_exp, pack_mma_frag(B, ow, m.cin, m.exp));
         }
         {   // depthwise [exp][1][k][k] -> [k*k][exp]
             const float* w = c.next(); BN bn = read_bn(c);
@@ -225,18 +243,21 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
             const float* w = c.next(); BN bn = read_bn(c);
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.cout, m.exp, 1, ow, ob);
             reg(&m.w_proj, ow); reg(&m.b_proj, ob);
+            reg(&m.wf_proj, pack_mma_frag(B, ow, m.exp, m.cout));
         }
     }
     {   // features.12
         const float* w = c.next(); BN bn = read_bn(c);
         pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, 576, 96, 1, ow, ob);
         reg(&p->w_last, ow); reg(&p->b_last, ob);
+        reg(&p->wf_last, pack_mma_frag(B, ow, 96, 576));
     }
     const int fpn_in[4] = {16, 24, 48, 576};
     for (int i = 0; i < 4; i++) {
         const float* w = c.next();
         pack_conv_kc(B, w, nullptr, nullptr, 0, 128, fpn_in[i], 1, ow, ob);
         reg(&p->w_lat[i], ow);
+        reg(&p->wf_lat[i], pack_mma_frag(B, ow, fpn_in[i], 128));
     }
     auto dense = [&](DenseConv& d, const float* w, const float* cb, const BN* bn, double eps, int cout, int cin, int k) {
         size_t off[4]; pack_dense(B, w, cb, bn, eps, cout, cin, k, off);

@@ -1,0 +1,239 @@
+// Batch-wide pointwise (1x1) convolution on tensor cores and batch-wide depthwise convolution, NHWC fp32.
+//   reference ops: every 1x1 conv of the trunk -- tv:models/mobilenetv3.py:87-108 (expand / project), features.12,
+//   dll/models/backbone.py:33-37 (FPN laterals + nearest top-down add) -- and tv:models/mobilenetv3.py:92-104 (depthwise).
+//
+// pw_mma_kernel: out[M][N] = act(A[M][K] * W[K][N] + bias) (+ residual), M = batch*H*W pixels.  CTA tile 128 pixels x
+// up to 128 output channels, 8 warps x 16 rows; A is streamed through shared memory in K chunks of 32 with register
+// prefetch (optionally scaled by the per-image SE excitation while it is staged); B fragments are pre-packed on the
+// host in mma.sync m16n8k8 order (hi/lo TF32 split) and come from L1/L2.  3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,
+// fp32 accumulate) keeps the trunk at fp32-level accuracy, which the channel top-k needs.
+#include "kpd_common.cuh"
+
+namespace kpd {
+
+__device__ __forceinline__ void mma_tf32_pw(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct PwMma {
+    const float* A; const float4* Wf; const float* bias; float* out;
+    int64_t M; int K, N, act;
+    const float* se_scale; int hw;           // optional [image][K] scale applied to A (SE excitation), hw = pixels/image
+    const float* res; int res_mode;          // 0 none, 1 same-shape add, 2 nearest-upsampled add (FPN top-down)
+    int H, W, up;                            // res_mode 2: output map H x W, coarse map (H/up) x (W/up), N channels
+    int round_tf32;                          // round the result to tf32 (it feeds a kind::tf32 tcgen05 MMA)
+};
+
+constexpr int PW_BM = 128, PW_KC = 32, PW_LDA = PW_KC + 4, PW_NT = 16, PW_THREADS = 256;
+
+__global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int tiles_m, int tiles_n) {
+    __shared__ __align__(16) float As[PW_BM * PW_LDA];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int n8 = p.N >> 3, K = p.K;
+    // staging map: thread loads float4 (row = tid/8 + 32*i, k4 = tid%8) for i = 0..3
+    const int sk4 = tid & 7, srow = tid >> 3;
+    const int total = tiles_m * tiles_n;
+
+    // persistent CTA: items (m-tile, n-chunk) are walked with a one-chunk-deep software pipeline -- the A chunk of the
+    // NEXT (item, k-chunk) is already in flight (registers) while the current one is multiplied / its tile is stored,
+    // so small-K GEMMs (K <= 32: a single chunk per tile) are bandwidth- instead of latency-bound.
+    auto load_chunk = [&](int item, int kc, float4 (&v)[4]) {
+        const int64_t m0 = (int64_t)(item / tiles_n) * PW_BM;
+        const int k = kc + sk4 * 4;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t m = m0 + srow + 32 * i;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < p.M && k < K) {
+                x = __ldg(reinterpret_cast<const float4*>(p.A + m * K + k));
+                if (p.se_scale) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.se_scale + (m / p.hw) * K + k));
+                    x.x *= sc.x; x.y *= sc.y; x.z *= sc.z; x.w *= sc.w;
+                }
+            }
+            v[i] = x;
+        }
+    };
+    float4 stage[4];
+    int item = blockIdx.x;
+    if (item < total) load_chunk(item, 0, stage);
+    for (; item < total; item += gridDim.x) {
+        const int64_t m0 = (int64_t)(item / tiles_n) * PW_BM;
+        const int nt0 = (item % tiles_n) * PW_NT, ntc = min(PW_NT, n8 - nt0);
+        float acc[PW_NT][4];
+#pragma unroll
+        for (int j = 0; j < PW_NT; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+        for (int kc = 0; kc < K; kc += PW_KC) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(As + (srow + 32 * i) * PW_LDA + sk4 * 4) = stage[i];
+            __syncthreads();
+            if (kc + PW_KC < K) load_chunk(item, kc + PW_KC, stage);
+            else if (item + (int)gridDim.x < total) load_chunk(item + gridDim.x, 0, stage);
+            const int ksteps = min(PW_KC, K - kc) >> 3;
+            const float* a0p = As + (warp * 16 + g) * PW_LDA + t;
+            const float* a1p = a0p + 8 * PW_LDA;
+            for (int ks = 0; ks < ksteps; ks++) {
+                const float av[4] = {a0p[ks * 8], a1p[ks * 8], a0p[ks * 8 + 4], a1p[ks * 8 + 4]};
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float h = tf32_rna(av[i]);
+                    ah[i] = __float_as_uint(h); al[i] = __float_as_uint(tf32_rna(av[i] - h));
+                }
+                const float4* wp = p.Wf + ((size_t)((kc >> 3) + ks) * n8 + nt0) * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < PW_NT; j++) {
+                    if (j < ntc) {
+                        const float4 b = __ldg(wp + j * 32);
+                        mma_tf32_pw(acc[j], al, __float_as_uint(b.x), __float_as_uint(b.y));
+                        mma_tf32_pw(acc[j], ah, __float_as_uint(b.z), __float_as_uint(b.w));
+                        mma_tf32_pw(acc[j], ah, __float_as_uint(b.x), __float_as_uint(b.y));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // epilogue: rows r0 = g, r1 = g + 8 of this warp's 16-row slab; columns n = (nt0+j)*8 + 2t, +1
+        const int64_t r[2] = {m0 + warp * 16 + g, m0 + warp * 16 + g + 8};
+        int64_t rbase[2] = {0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (r[h] >= p.M) continue;
+            if (p.res_mode == 1) rbase[h] = r[h] * p.N;
+            else if (p.res_mode == 2) {
+                const int x = (int)(r[h] % p.W), y = (int)((r[h] / p.W) % p.H); const int64_t b = r[h] / ((int64_t)p.W * p.H);
+                rbase[h] = ((b * (p.H / p.up) + y / p.up) * (p.W / p.up) + x / p.up) * p.N;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PW_NT; j++) {
+            if (j >= ntc) break;
+            const int n = (nt0 + j) * 8 + 2 * t;
+            const float b0 = p.bias ? __ldg(p.bias + n) : 0.f, b1 = p.bias ? __ldg(p.bias + n + 1) : 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (r[h] >= p.M) continue;
+                float v0 = apply_act(acc[j][2 * h] + b0, p.act), v1 = apply_act(acc[j][2 * h + 1] + b1, p.act);
+                if (p.res_mode) {
+                    const float2 q = __ldg(reinterpret_cast<const float2*>(p.res + rbase[h] + n));
+                    v0 += q.x; v1 += q.y;
+                }
+                if (p.round_tf32) { v0 = tf32_rna(v0); v1 = tf32_rna(v1); }
+                *reinterpret_cast<float2*>(p.out + r[h] * p.N + n) = make_float2(v0, v1);
+            }
+        }
+    }
+}
+
+int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s) {
+    if ((p.K & 7) || (p.N & 7)) { set_error("pointwise_mma: K and N must be multiples of 8 (got %d, %d)", p.K, p.N); return KPD_ERR_UNSUPPORTED; }
+    if (p.M <= 0) return 0;
+    const int tiles_m = (int)((p.M + PW_BM - 1) / PW_BM), tiles_n = ((p.N >> 3) + PW_NT - 1) / PW_NT;
+    const int grid = (int)std::min<int64_t>((int64_t)tiles_m * tiles_n, (int64_t)sm_count * 2);
+    pw_mma_kernel<<<grid, PW_THREADS, 0, s>>>(p, tiles_m, tiles_n);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depthwise k x k conv (+ folded BN + act), NHWC fp32, batch-wide, shared-memory tiled; optional SE squeeze.
+// CTA = (image, group of <= 32 channels, TH x TW output tile).  The zero-padded input tile (with halo) and the group's
+// tap weights are staged in shared memory once (coalesced float4), so the k*k tap loop is branch-free LDS + FMA.  A thread
+// keeps one 4-channel group (256 % channels-per-group/4 == 0), so the squeeze accumulates in registers; one shared atomic
+// per thread and one global atomic per (CTA, channel) finish it.
+template <int K>
+__global__ void __launch_bounds__(256, 2) dw_tiled_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out,
+                                                       float* __restrict__ pool, int H, int C, int stride, int act,
+                                                       int TH, int TW, int tiles_x, int CG) {
+    extern __shared__ __align__(16) float smem[];
+    const int Ho = H / stride, pad = (K - 1) / 2;
+    const int b = blockIdx.z, c0 = blockIdx.y * CG, cg = min(CG, C - c0), cg4 = cg >> 2;
+    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TW;
+    const int th = min(TH, Ho - ty0), tw = min(TW, Ho - tx0);
+    const int in_h = (th - 1) * stride + K, in_w = (tw - 1) * stride + K;
+    float* tile = smem;                                   // [in_h][in_w][cg]
+    float* wsm = smem + (size_t)((TH - 1) * stride + K) * ((TW - 1) * stride + K) * CG;   // [K*K][cg]
+    float* red = wsm + K * K * CG;                        // [cg]
+    const int tid = threadIdx.x;
+    const int iy0 = ty0 * stride - pad, ix0 = tx0 * stride - pad;
+    const float* inb = in + (size_t)b * H * H * C + c0;
+    for (int i = tid; i < in_h * in_w * cg4; i += 256) {
+        const int c4 = i % cg4, pxl = i / cg4;
+        const int yy = pxl / in_w, xx = pxl - yy * in_w;
+        const int iy = iy0 + yy, ix = ix0 + xx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < H) v = __ldg(reinterpret_cast<const float4*>(inb + ((size_t)iy * H + ix) * C) + c4);
+        reinterpret_cast<float4*>(tile + (size_t)pxl * cg)[c4] = v;
+    }
+    for (int i = tid; i < K * K * cg4; i += 256) {
+        const int c4 = i % cg4, tp = i / cg4;
+        reinterpret_cast<float4*>(wsm + tp * cg)[c4] = __ldg(reinterpret_cast<const float4*>(w + (size_t)tp * C + c0) + c4);
+    }
+    if (tid < cg) red[tid] = 0.f;
+    __syncthreads();
+    const int c4 = tid % cg4;                             // fixed for the thread: 256 % cg4 == 0
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + c4);
+    float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* outb = out + (size_t)b * Ho * Ho * C + c0;
+    for (int item = tid; item < th * tw * cg4; item += 256) {
+        const int q = item / cg4;
+        const int oy = q / tw, ox = q - oy * tw;
+        const float* tp = tile + ((size_t)(oy * stride) * in_w + ox * stride) * cg + c4 * 4;
+        float4 acc = bb;
+#pragma unroll
+        for (int ky = 0; ky < K; ky++) {
+#pragma unroll
+            for (int kx = 0; kx < K; kx++) {
+                const float4 v = *reinterpret_cast<const float4*>(tp + ((size_t)ky * in_w + kx) * cg);
+                const float4 ww = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * cg + c4 * 4);
+                acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+                acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+            }
+        }
+        float4 r;
+        r.x = apply_act(acc.x, act); r.y = apply_act(acc.y, act); r.z = apply_act(acc.z, act); r.w = apply_act(acc.w, act);
+        reinterpret_cast<float4*>(outb + ((size_t)(ty0 + oy) * Ho + tx0 + ox) * C)[c4] = r;
+        ssum.x += r.x; ssum.y += r.y; ssum.z += r.z; ssum.w += r.w;
+    }
+    if (pool) {
+        atomicAdd(&red[c4 * 4 + 0], ssum.x); atomicAdd(&red[c4 * 4 + 1], ssum.y);
+        atomicAdd(&red[c4 * 4 + 2], ssum.z); atomicAdd(&red[c4 * 4 + 3], ssum.w);
+        __syncthreads();
+        if (tid < cg) atomicAdd(pool + (size_t)b * C + c0 + tid, red[tid]);
+    }
+}
+
+int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s) {
+    const int Ho = H / m.stride, C = m.exp;
+    if (C & 3) { set_error("depthwise_batched: unsupported channel count %d", C); return KPD_ERR_UNSUPPORTED; }
+    // channel group: <= 32 channels with (group/4) dividing 256 for every group incl. the last partial one
+    int CG = 32;
+    if (C < 32) CG = C;
+    else if ((C % 32) != 0 && (256 % ((C % 32) / 4)) != 0) CG = 16;
+    if (256 % (CG / 4) != 0 || (C % CG != 0 && 256 % ((C % CG) / 4) != 0)) { set_error("depthwise_batched: channel grouping failed for C=%d", C); return KPD_ERR_UNSUPPORTED; }
+    // output tile: full width up to 28, height so that the input tile stays <= ~40 KB
+    const int TW = std::min(Ho, 28);
+    int TH = std::min(Ho, 28);
+    while (TH > 1 && (size_t)((TH - 1) * m.stride + m.k) * ((TW - 1) * m.stride + m.k) * CG * 4 > 40 * 1024) TH--;
+    int tiles_y = (Ho + TH - 1) / TH;
+    TH = (Ho + tiles_y - 1) / tiles_y;                    // balance the row tiles
+    const int tiles_x = (Ho + TW - 1) / TW;
+    const size_t smem = sizeof(float) * ((size_t)((TH - 1) * m.stride + m.k) * ((TW - 1) * m.stride + m.k) * CG + (size_t)m.k * m.k * CG + CG);
+    dim3 grid(tiles_x * tiles_y, (C + CG - 1) / CG, B);
+    (void)sm_count;
+    static bool attr = false;
+    if (!attr) {
+        KPD_CUDA(cudaFuncSetAttribute(dw_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        KPD_CUDA(cudaFuncSetAttribute(dw_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr = true;
+    }
+    if (m.k == 3) dw_tiled_kernel<3><<<grid, 256, smem, s>>>(in, m.w_dw, m.b_dw, out, pool, H, C, m.stride, m.act, TH, TW, tiles_x, CG);
+    else          dw_tiled_kernel<5><<<grid, 256, smem, s>>>(in, m.w_dw, m.b_dw, out, pool, H, C, m.stride, m.act, TH, TW, tiles_x, CG);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace kpd
