@@ -123,6 +123,11 @@ int  kpd_channel_topk(const kpd_plan* plan, int batch, void* d_workspace, const 
 int  kpd_roi_head(const kpd_plan* plan, int precision, int batch, int size, const float* d_boxes, int persons,
                   const int32_t* d_topk_override, float* d_heatmap, float* d_keypoints, float* d_visibilities,
                   void* d_workspace, const kpd_workspace_layout* layout, void* stream);
+/* keypoint_model.py:212-228 extract_roi_features (tv roi_align, aligned=False, adaptive sampling) as a leaf op:
+ * d_feat fp32 NHWC [B,H,W,128], d_channels int32 [B,64] (channels to gather per image), d_boxes fp32 [n,4] normalised
+ * cx,cy,w,h, d_roi_batch int32 [n] -> d_out fp32 NHWC [n,56,56,64].  d_partials: scratch of n*28*2*64 floats. */
+int  kpd_roi_align(const float* d_feat, const int32_t* d_channels, const float* d_boxes, const int32_t* d_roi_batch,
+                   int n, int height, int width, float* d_out, float* d_partials, void* stream);
 /* heatmap_head.py:81-113 on caller-supplied ROI features: d_x fp32 NCHW [n,64,56,56] ->
  * d_heatmaps fp32 NCHW [n,17,56,56], d_cw fp32 [n,64], d_sw fp32 [n,56,56] (either may be NULL). */
 int  kpd_heatmap_head(const kpd_plan* plan, int precision, const float* d_x, int n, float* d_heatmaps,

@@ -178,25 +178,62 @@ __global__ void __launch_bounds__(256, 2) dw_tiled_kernel(const float* __restric
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c0) + c4);
     float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f);
     float* outb = out + (size_t)b * Ho * Ho * C + c0;
-    for (int item = tid; item < th * tw * cg4; item += 256) {
+    // Sliding window: an item is a run of XR consecutive outputs of one row for one 4-channel group.  Per tap row the
+    // (XR-1)*stride+K input vectors and the K weights are loaded from shared memory once and reused from registers
+    // (~3x fewer LDS than one load pair per tap; the plain form is shared-memory-bandwidth bound).
+    constexpr int XR = 4;
+    const int runs = (tw + XR - 1) / XR;
+    for (int item = tid; item < th * runs * cg4; item += 256) {
         const int q = item / cg4;
-        const int oy = q / tw, ox = q - oy * tw;
-        const float* tp = tile + ((size_t)(oy * stride) * in_w + ox * stride) * cg + c4 * 4;
-        float4 acc = bb;
+        const int oy = q / runs, ox0 = (q - oy * runs) * XR;
+        float4 acc[XR];
 #pragma unroll
-        for (int ky = 0; ky < K; ky++) {
+        for (int j = 0; j < XR; j++) acc[j] = bb;
+        if (stride == 1) {
+            constexpr int SEG = XR - 1 + K;
 #pragma unroll
-            for (int kx = 0; kx < K; kx++) {
-                const float4 v = *reinterpret_cast<const float4*>(tp + ((size_t)ky * in_w + kx) * cg);
-                const float4 ww = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * cg + c4 * 4);
-                acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-                acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+            for (int ky = 0; ky < K; ky++) {
+                const float* rp = tile + ((size_t)(oy + ky) * in_w + ox0) * cg + c4 * 4;
+                float4 seg[SEG], wk[K];
+#pragma unroll
+                for (int i = 0; i < SEG; i++) seg[i] = *reinterpret_cast<const float4*>(rp + (size_t)i * cg);   // a partial last run over-reads into the weight area: unused lanes
+#pragma unroll
+                for (int kx = 0; kx < K; kx++) wk[kx] = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * cg + c4 * 4);
+#pragma unroll
+                for (int j = 0; j < XR; j++)
+#pragma unroll
+                    for (int kx = 0; kx < K; kx++) {
+                        acc[j].x = fmaf(seg[j + kx].x, wk[kx].x, acc[j].x); acc[j].y = fmaf(seg[j + kx].y, wk[kx].y, acc[j].y);
+                        acc[j].z = fmaf(seg[j + kx].z, wk[kx].z, acc[j].z); acc[j].w = fmaf(seg[j + kx].w, wk[kx].w, acc[j].w);
+                    }
+            }
+        } else {
+            constexpr int SEG = (XR - 1) * 2 + K;
+#pragma unroll
+            for (int ky = 0; ky < K; ky++) {
+                const float* rp = tile + ((size_t)(oy * 2 + ky) * in_w + ox0 * 2) * cg + c4 * 4;
+                float4 seg[SEG], wk[K];
+#pragma unroll
+                for (int i = 0; i < SEG; i++) seg[i] = *reinterpret_cast<const float4*>(rp + (size_t)i * cg);   // a partial last run over-reads into the weight area: unused lanes
+#pragma unroll
+                for (int kx = 0; kx < K; kx++) wk[kx] = *reinterpret_cast<const float4*>(wsm + (ky * K + kx) * cg + c4 * 4);
+#pragma unroll
+                for (int j = 0; j < XR; j++)
+#pragma unroll
+                    for (int kx = 0; kx < K; kx++) {
+                        acc[j].x = fmaf(seg[2 * j + kx].x, wk[kx].x, acc[j].x); acc[j].y = fmaf(seg[2 * j + kx].y, wk[kx].y, acc[j].y);
+                        acc[j].z = fmaf(seg[2 * j + kx].z, wk[kx].z, acc[j].z); acc[j].w = fmaf(seg[2 * j + kx].w, wk[kx].w, acc[j].w);
+                    }
             }
         }
-        float4 r;
-        r.x = apply_act(acc.x, act); r.y = apply_act(acc.y, act); r.z = apply_act(acc.z, act); r.w = apply_act(acc.w, act);
-        reinterpret_cast<float4*>(outb + ((size_t)(ty0 + oy) * Ho + tx0 + ox) * C)[c4] = r;
-        ssum.x += r.x; ssum.y += r.y; ssum.z += r.z; ssum.w += r.w;
+#pragma unroll
+        for (int j = 0; j < XR; j++) {
+            if (ox0 + j >= tw) break;
+            float4 r;
+            r.x = apply_act(acc[j].x, act); r.y = apply_act(acc[j].y, act); r.z = apply_act(acc[j].z, act); r.w = apply_act(acc[j].w, act);
+            reinterpret_cast<float4*>(outb + ((size_t)(ty0 + oy) * Ho + tx0 + ox0 + j) * C)[c4] = r;
+            ssum.x += r.x; ssum.y += r.y; ssum.z += r.z; ssum.w += r.w;
+        }
     }
     if (pool) {
         atomicAdd(&red[c4 * 4 + 0], ssum.x); atomicAdd(&red[c4 * 4 + 1], ssum.y);

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
                                                         const int32_t* __restrict__ roi_count, float* __restrict__ roi_feat,
                                                         float* __restrict__ part, int H, int W) {
     const int n = blockIdx.y;
-    if (n >= *roi_count) return;
+    if (roi_count && n >= *roi_count) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = roi_batch[n];
     const float4 bx = reinterpret_cast<const float4*>(roi_box)[n];
@@ -233,3 +233,14 @@ int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16,
 }
 
 }  // namespace kpd
+
+extern "C" int kpd_roi_align(const float* d_feat, const int32_t* d_channels, const float* d_boxes, const int32_t* d_roi_batch,
+                             int n, int height, int width, float* d_out, float* d_partials, void* stream) {
+    KPD_CHECK_ARG(n >= 0 && n <= 65535 && height > 0 && width > 0, "kpd_roi_align: bad sizes");
+    if (n == 0) return 0;
+    KPD_CHECK_ARG(d_feat && d_channels && d_boxes && d_roi_batch && d_out && d_partials, "kpd_roi_align: null pointer");
+    kpd::roi_align_kernel<<<dim3(kpd::ROI_PARTS, n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_feat, d_channels, d_boxes, d_roi_batch, nullptr, d_out, d_partials, height, width);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}

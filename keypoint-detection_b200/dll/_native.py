@@ -49,6 +49,7 @@ _SIGNATURES = {
     "kpd_channel_topk": (C.c_int, [_P, C.c_int, _P, C.POINTER(WorkspaceLayout), _P]),
     "kpd_roi_head": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P,
                                C.POINTER(WorkspaceLayout), _P]),
+    "kpd_roi_align": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "kpd_heatmap_head": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.POINTER(WorkspaceLayout), _P]),
     "kpd_decode": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
                              _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -177,7 +177,31 @@ class MultiPersonKeypointModel(nn.Module):
         return torch.stack([xs, ys], dim=-1).view(shape)
 
     def extract_roi_features(self, features: torch.Tensor, box: torch.Tensor, output_size: Tuple[int, int] = (56, 56)):
-        raise NotImplementedError("ROI-align runs fused inside forward(); the standalone method is not part of the hot path")
+        """keypoint_model.py:212-228: features [1,C,H,W], box [cx,cy,w,h] normalised -> [1,C,56,56] (legacy roi_align).
+
+        Stand-alone form of the ROI-align kernel that forward() runs batched: channels are processed in slabs of 128
+        (the kernel's NHWC tile) with two 64-channel gathers per slab."""
+        if tuple(output_size) != (56, 56):
+            raise NotImplementedError("the CUDA ROI-align kernel is built for the reference's default 56x56 output")
+        dev = N.require_cuda(features.device if features.is_cuda else None)
+        with torch.cuda.device(dev):
+            f = as_cuda_f32(features, dev)
+            _, Cc, H, W = f.shape
+            bx = as_cuda_f32(box.reshape(1, 4), dev)
+            rb = torch.zeros(1, dtype=torch.int32, device=dev)
+            part = torch.empty(28 * 2 * 64, dtype=torch.float32, device=dev)
+            outs = []
+            for c0 in range(0, Cc, 128):
+                slab = torch.zeros(1, H, W, 128, device=dev, dtype=torch.float32)
+                cs = min(128, Cc - c0)
+                slab[..., :cs] = f[:, c0:c0 + cs].permute(0, 2, 3, 1)
+                for h0 in range(0, cs, 64):
+                    idx = (torch.arange(64, device=dev, dtype=torch.int32) + h0).clamp(max=127).view(1, 64).contiguous()
+                    o = torch.empty(1, 56, 56, 64, device=dev, dtype=torch.float32)
+                    N.check(N.load().kpd_roi_align(N.ptr(slab), N.ptr(idx), N.ptr(bx), N.ptr(rb), 1, H, W, N.ptr(o), N.ptr(part),
+                                                   N.stream_ptr(dev)), "kpd_roi_align")
+                    outs.append(o[..., :min(64, cs - h0)].permute(0, 3, 1, 2))
+        return torch.cat(outs, dim=1)
 
 
 def box_center_to_corners(box):

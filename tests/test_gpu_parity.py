@@ -341,6 +341,21 @@ def test_nms_and_iou_bit_exact(model):
         np.testing.assert_array_equal(keep[i, :count[i]], want)
 
 
+def test_extract_roi_features_matches_torchvision_golden(model):
+    """Stand-alone ROI-align method (A5) against torchvision's own outputs (tests/golden/roi_align.npz)."""
+    g = _golden("roi_align.npz")
+    feat = torch.from_numpy(g["feat"])                      # [2,8,64,64]
+    for i, roi in enumerate(g["rois"]):
+        b = int(roi[0]); x1, y1, x2, y2 = [float(v) / 64.0 for v in roi[1:]]
+        box = torch.tensor([(x1 + x2) / 2, (y1 + y2) / 2, x2 - x1, y2 - y1], dtype=torch.float32)
+        corners = torch.stack([box[0] - box[2] / 2, box[1] - box[3] / 2, box[0] + box[2] / 2, box[1] + box[3] / 2]).clamp(0, 1) * 64
+        want = OM.roi_align_legacy(feat[b], corners.view(1, 4).numpy())[0].numpy()   # oracle on the exact corners the method derives
+        got = model.extract_roi_features(feat[b:b + 1], box)[0].cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=5e-5)      # sample coordinates differ by 1 ulp (FMA contraction)
+        if np.allclose(corners.numpy(), roi[1:], atol=1e-4):
+            np.testing.assert_allclose(got, g["out"][i], rtol=1e-4, atol=1e-4)
+
+
 def test_person_heads(model, sd):
     g = _golden("person_heads.npz")
     box, cls = model.person_detector.heads(torch.from_numpy(g["x"]), level=0)
