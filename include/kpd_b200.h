@@ -133,6 +133,11 @@ int  kpd_roi_align(const float* d_feat, const int32_t* d_channels, const float* 
 int  kpd_heatmap_head(const kpd_plan* plan, int precision, const float* d_x, int n, float* d_heatmaps,
                       float* d_cw, float* d_sw, void* d_workspace, const kpd_workspace_layout* layout, void* stream);
 
+/* Leaf access to the dense 3x3 convolutions (fpn_convs[0]: conv 0; head convs: 1..3), bias + ReLU fused.
+ * impl 0: fp32 CUDA cores, 1: tcgen05 tf32, 2: tcgen05 bf16 (all NHWC), 3 / 4: tap-reuse tcgen05 tf32 / bf16 with the
+ * input in chunk-major layout [n][C/E][h][w][E] (E = 16 bytes of channels) and NHWC output. */
+int  kpd_dense_conv(const kpd_plan* plan, int conv, int impl, const void* d_in, void* d_out, int n, int h, int w, void* stream);
+
 /* ---- standalone decoders: heatmap_head.py:265-413 and keypoint_model.py:250-313 ------------------
  * d_heatmaps [N,K,H,W], dtype 0 = fp32, 1 = bf16.  Any output pointer may be NULL.
  *   d_argmax int32 [N,K] flat index of the first maximum;  d_maxval fp32 [N,K]

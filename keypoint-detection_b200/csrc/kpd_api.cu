@@ -16,6 +16,8 @@ int run_dummy_person(const int32_t* img_count, float* vis, int B, int P, int K, 
 int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int conv_dense_umma_halo(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
+                         int out_cm, int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s);
 int pointwise_ex(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
                  int act, int hw, int out_nchw, cudaStream_t s);
 
@@ -248,4 +250,22 @@ extern "C" int kpd_fpn_levels123(const kpd_plan* plan, int B, int S, void* d_wor
         KPD_TRY(conv_dense_simt(plan->fpn_conv[i], reinterpret_cast<const float*>(ws + L.scratch + lat_off[i]), d_out[i], B, hs[i], hs[i], ACT_RELU, nullptr, s));
     }
     return 0;
+}
+
+// Leaf access to the dense 3x3 convolutions (unit tests / micro-benchmarks of the tensor-core kernels).
+// conv: 0 = fpn_convs[0], 1..3 = head convs.  impl: 0 = fp32 CUDA cores (NHWC fp32 in/out), 1 = tcgen05 tf32 (NHWC fp32),
+// 2 = tcgen05 bf16 (NHWC bf16), 3 = tap-reuse tcgen05 tf32 (chunk-major fp32 in, NHWC fp32 out), 4 = tap-reuse bf16
+// (chunk-major bf16 in, NHWC bf16 out).  All with bias + ReLU.
+extern "C" int kpd_dense_conv(const kpd_plan* plan, int conv, int impl, const void* d_in, void* d_out, int n, int h, int w, void* stream) {
+    KPD_CHECK_ARG(plan && d_in && d_out, "kpd_dense_conv: null argument");
+    KPD_CHECK_ARG(conv >= 0 && conv <= 3 && impl >= 0 && impl <= 4 && n > 0 && h > 0 && w > 0, "kpd_dense_conv: bad argument");
+    const DenseConv& c = conv == 0 ? plan->fpn_conv[0] : plan->head_conv[conv - 1];
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (impl) {
+        case 0: return conv_dense_simt(c, static_cast<const float*>(d_in), static_cast<float*>(d_out), n, h, w, ACT_RELU, nullptr, s);
+        case 1: return conv_dense_umma(plan, c, 0, d_in, d_out, 0, n, h, w, ACT_RELU, 0, nullptr, s);
+        case 2: return conv_dense_umma(plan, c, 1, d_in, d_out, 1, n, h, w, ACT_RELU, 0, nullptr, s);
+        case 3: return conv_dense_umma_halo(plan, c, 0, d_in, d_out, 0, 0, n, h, w, ACT_RELU, 0, nullptr, s);
+        default: return conv_dense_umma_halo(plan, c, 1, d_in, d_out, 1, 0, n, h, w, ACT_RELU, 0, nullptr, s);
+    }
 }

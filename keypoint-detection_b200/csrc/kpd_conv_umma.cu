@@ -89,10 +89,53 @@ struct ConvParams {
     int tw, th, tn;                    // pixel box of one 128-row tile: tw*th*tn == 128
     int tiles_w, tiles_h, tiles_n;
     int act, out_bf16, stages, round_out_tf32;
+    int out_cm;                        // 1: write [N][Cout/E16][H][W][E16] (16-byte channel chunks, the halo kernel's input layout)
     const float* bias;
     void* out;                         // NHWC [N,H,W,Cout], bf16 or fp32
     const int32_t* n_valid;            // optional device count of live instances (<= N)
 };
+
+// Store 32 consecutive output channels (c0..c0+31) of pixel (n,h,w): NHWC bf16 / fp32, or chunk-major (16-byte chunks).
+__device__ __forceinline__ void epi_store(const ConvParams& p, const float (&v)[32], int n, int h, int w, size_t pix, int c0) {
+    if (p.out_cm) {                 // chunk-major: 16-byte chunk q of channel block c0 -> plane (c0*elt/16 + q)
+        const size_t plane = (size_t)p.H * p.W;
+        if (p.out_bf16) {
+            uint4* o = reinterpret_cast<uint4*>(p.out) + ((size_t)n * (p.Cout >> 3) + (c0 >> 3)) * plane + (size_t)h * p.W + w;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 u;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+                u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+                o[(size_t)q * plane] = u;
+            }
+        } else {
+            float4* o = reinterpret_cast<float4*>(p.out) + ((size_t)n * (p.Cout >> 2) + (c0 >> 2)) * plane + (size_t)h * p.W + w;
+#pragma unroll
+            for (int q = 0; q < 8; q++) o[(size_t)q * plane] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    } else if (p.out_bf16) {
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint4 u;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+            u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+            o[q] = u;
+        }
+    } else {
+        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + c0);
+#pragma unroll
+        for (int q = 0; q < 8; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
 
 constexpr int UMMA_THREADS = 192;
 constexpr int A_BYTES = 128 * 128;     // 128 rows x 128 bytes
@@ -214,29 +257,168 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         x = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
                         v[j] = p.round_out_tf32 ? tf32_rna(x) : x;
                     }
-                    if (p.out_bf16) {
-                        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.Cout + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            uint4 u;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
-                            __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
-                            __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-                            u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
-                            u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
-                            o[q] = u;
-                        }
-                    } else {
-                        float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.Cout + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
+                    epi_store(p, v, n, h, w, pix, c0);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tap-reuse variant
+// conv_umma_halo_kernel: the classic kernel re-loads the A operand for each of the 9 taps, which makes N <= 128 convs
+// (FPN-0, head conv3) L2->SMEM bandwidth bound.  Here the input lives in a chunk-major layout [N][C/E16][H][W][E16]
+// (E16 = elements per 16 bytes) and ONE TMA box {10*E16, 18, 8 chunks} brings an (8+2)x(16+2) pixel halo tile of a
+// 128-byte channel slab into shared memory as [chunk][row][col][16 B] -- exactly the canonical NO-SWIZZLE K-major UMMA
+// layout for an 8-wide x 16-high output tile (core matrix = 8 pixels of a row x 16 B; SBO = halo row pitch = 160 B;
+// LBO = chunk plane = 2880 B).  Every tap is then just a different descriptor start address (+ (ky*10+kx)*16 B), so
+// the 23 KB slab is read from L2 once and used by 9 x 4 MMAs.  Weights stream per tap as before (128B-swizzled).
+constexpr int HALO_W = 10, HALO_H = 18, HALO_CHUNK = HALO_W * HALO_H * 16;   // bytes per 16-byte-channel plane
+constexpr int HALO_SLAB = 8 * HALO_CHUNK;                                    // 8 chunks = 128 bytes of channels
+
+__device__ __forceinline__ uint64_t make_sdesc_noswz(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(HALO_CHUNK >> 4) << 16) | ((uint64_t)((HALO_W * 16) >> 4) << 32) | (1ull << 46);
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(UMMA_THREADS, 1)
+conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p,
+                      int a_stages, int b_stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int B_BYTES = p.Cout * 128;
+    uint8_t* smB = smem;                                           // [b_stages][Cout*128]   (1024-aligned: swizzled)
+    uint8_t* smA = smem + (size_t)b_stages * B_BYTES;              // [a_stages][HALO_SLAB]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smA + (size_t)a_stages * HALO_SLAB);
+    // bars: a_full[a], a_empty[a], b_full[b], b_empty[b], tmem_full[2], tmem_empty[2]
+    const int AS = a_stages, BS = b_stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * AS + 2 * BS + 4);
+    float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto afull = [&](int i) { return bar0 + 8u * i; };
+    auto aempty = [&](int i) { return bar0 + 8u * (AS + i); };
+    auto bfull = [&](int i) { return bar0 + 8u * (2 * AS + i); };
+    auto bempty = [&](int i) { return bar0 + 8u * (2 * AS + BS + i); };
+    auto tfull = [&](int i) { return bar0 + 8u * (2 * AS + 2 * BS + i); };
+    auto tempty = [&](int i) { return bar0 + 8u * (2 * AS + 2 * BS + 2 + i); };
+    int tmem_cols = 32; while (tmem_cols < 2 * p.Cout) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int i = 0; i < AS; i++) { mbar_init(afull(i), 1); mbar_init(aempty(i), 1); }
+        for (int i = 0; i < BS; i++) { mbar_init(bfull(i), 1); mbar_init(bempty(i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull(i), 1); mbar_init(tempty(i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_live = p.n_valid ? min(*p.n_valid, p.N) : p.N;
+    const int total_tiles = n_live * p.tiles_h * p.tiles_w;
+    constexpr int BK = BF16 ? 64 : 32;                 // channels per 128-byte slab
+    constexpr int E16 = BF16 ? 8 : 4;                  // elements per 16-byte chunk
+    const int slabs = p.Cin / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {                                // ---------------- TMA producer (A slabs + per-tap weight tiles)
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+                for (int sl = 0; sl < slabs; sl++) {
+                    mbar_wait(aempty(as), aph ^ 1);
+                    mbar_expect_tx(afull(as), (uint32_t)HALO_SLAB);
+                    // coords: {element in the W*E16 row, h, chunk, n}; negative / past-the-end coordinates are zero-filled
+                    tma_load_4d(smem_u32(smA + (size_t)as * HALO_SLAB), &tmA, afull(as), (iw * 8 - 1) * E16, ih * 16 - 1, sl * 8, n);
+                    if (++as == AS) { as = 0; aph ^= 1; }
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(bempty(bs), bph ^ 1);
+                        mbar_expect_tx(bfull(bs), (uint32_t)B_BYTES);
+                        tma_load_2d(smem_u32(smB + (size_t)bs * B_BYTES), &tmB, bfull(bs), tap * p.Cin + sl * BK, 0);
+                        if (++bs == BS) { bs = 0; bph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                // ---------------- MMA issuer
+            const uint32_t fmt = BF16 ? 1u : 2u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+            int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+                for (int sl = 0; sl < slabs; sl++) {
+                    mbar_wait(afull(as), aph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smA + (size_t)as * HALO_SLAB);
+                    for (int tap = 0; tap < 9; tap++) {
+                        mbar_wait(bfull(bs), bph);
+                        tc_fence_after();
+                        const uint64_t adesc = make_sdesc_noswz(sa + (uint32_t)((tap / 3) * HALO_W + tap % 3) * 16u);
+                        const uint64_t bdesc = make_sdesc(smem_u32(smB + (size_t)bs * B_BYTES));
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; k4++)  // 32 bytes of K = two 16-byte chunk planes per MMA
+                            tc_mma<BF16>(d_tmem, adesc + (uint64_t)((2 * k4 * HALO_CHUNK) >> 4), bdesc + 2 * k4, idesc, (sl | tap | k4) != 0 ? 1u : 0u);
+                        tc_commit(bempty(bs));
+                        if (++bs == BS) { bs = 0; bph ^= 1; }
+                    }
+                    tc_commit(aempty(as));
+                    if (++as == AS) { as = 0; aph ^= 1; }
+                }
+                tc_commit(tfull(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {                                            // ---------------- epilogue warps 2..5
+        const int lg = warp & 3;
+        const int row = lg * 32 + lane;
+        const int rw = row & 7, rh = row >> 3;          // 8-wide x 16-high output tile
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+            const int w = iw * 8 + rw, h = ih * 16 + rh;
+            const bool valid = (w < p.W) && (h < p.H);
+            const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+            mbar_wait(tfull(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.Cout);
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                uint32_t r[32];
+                tc_ld32(taddr + c0, r);
+                tc_wait_ld();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        float x = __uint_as_float(r[j]) + sbias[c0 + j];
+                        x = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
+                        v[j] = p.round_out_tf32 ? tf32_rna(x) : x;
+                    }
+                    epi_store(p, v, n, h, w, pix, c0);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -314,6 +496,62 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     } else {
         KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conv_umma_kernel<false><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);
+    }
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+// Tap-reuse launcher.  `in` is chunk-major [N][Cin/E16][H][W][E16]; taps must be 9.
+int conv_dense_umma_halo(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
+                         int out_cm, int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s) {
+    if (N <= 0) return 0;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
+    const int elt = prec_bf16 ? 2 : 4, E16 = 16 / elt, BK = 128 / elt;
+    if (c.taps != 9 || c.cin % BK != 0 || c.cout % 16 != 0 || c.cout > 256 || c.cout < 16) { set_error("conv_dense_umma_halo: unsupported conv %d->%d taps %d", c.cin, c.cout, c.taps); return KPD_ERR_UNSUPPORTED; }
+    ConvParams p{};
+    p.N = N; p.H = H; p.W = W; p.Cin = c.cin; p.Cout = c.cout; p.taps = 9;
+    p.tw = 8; p.th = 16; p.tn = 1;
+    p.tiles_w = (W + 7) / 8; p.tiles_h = (H + 15) / 16; p.tiles_n = N;
+    p.act = act; p.round_out_tf32 = round_out_tf32; p.out_bf16 = out_bf16; p.out_cm = out_cm; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
+    const int b_bytes = c.cout * 128;
+    const int a_stages = 3;
+    const int misc = 1024 + 8 * (2 * 3 + 2 * 8 + 4) + 16 + 4 * c.cout + 64;
+    int b_stages = (227 * 1024 - misc - a_stages * HALO_SLAB) / b_bytes; if (b_stages > 8) b_stages = 8;
+    if (b_stages < 2) { set_error("conv_dense_umma_halo: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
+    const size_t smem = (size_t)b_stages * b_bytes + (size_t)a_stages * HALO_SLAB + misc;
+    CUtensorMap tmA, tmB;
+    {
+        const cuuint64_t CH = (cuuint64_t)c.cin / E16;
+        cuuint64_t dims[4] = {(cuuint64_t)W * E16, (cuuint64_t)H, CH, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, CH * H * W * 16};
+        cuuint32_t box[4] = {(cuuint32_t)(HALO_W * E16), (cuuint32_t)HALO_H, 8, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                         const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A halo) failed: %d", (int)r); return KPD_ERR_STATE; }
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)9 * c.cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)c.cout};
+        cuuint64_t strides[1] = {K * elt};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)c.cout};
+        cuuint32_t es[2] = {1, 1};
+        const void* wptr = prec_bf16 ? static_cast<const void*>(c.w_bf16) : static_cast<const void*>(c.w_tf32);
+        CUresult r = enc(&tmB, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<void*>(wptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return KPD_ERR_STATE; }
+    }
+    const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int grid = std::min(total_tiles, plan->sm_count);
+    if (prec_bf16) {
+        KPD_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_umma_halo_kernel<true><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p, a_stages, b_stages);
+    } else {
+        KPD_CUDA(cudaFuncSetAttribute(conv_umma_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conv_umma_halo_kernel<false><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p, a_stages, b_stages);
     }
     KPD_LAUNCH_CHECK();
     return 0;

@@ -28,54 +28,72 @@ struct PwMma {
 
 constexpr int PW_BM = 128, PW_KC = 32, PW_LDA = PW_KC + 4, PW_NT = 16, PW_THREADS = 256;
 
+constexpr int PW_STAGES = 4;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;                       // src-size 0 => 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+
+// Persistent CTAs walk the (m-tile, n-chunk) items; the A operand streams through a 4-stage cp.async ring that runs
+// up to 3 K-chunks (or whole tiles, when K <= 32) ahead of the MMAs, across item boundaries -- so the many small-K GEMMs
+// of the trunk are bandwidth- instead of latency-bound.  The SE excitation (a per-image, per-input-channel factor) is
+// applied to the A fragments as they are read from shared memory.
 __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int tiles_m, int tiles_n) {
-    __shared__ __align__(16) float As[PW_BM * PW_LDA];
+    extern __shared__ __align__(16) float As_all[];      // [PW_STAGES][PW_BM * PW_LDA]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int n8 = p.N >> 3, K = p.K;
-    // staging map: thread loads float4 (row = tid/8 + 32*i, k4 = tid%8) for i = 0..3
-    const int sk4 = tid & 7, srow = tid >> 3;
+    const int sk4 = tid & 7, srow = tid >> 3;            // staging map: float4 (row = srow + 32*i, k4 = sk4), i = 0..3
     const int total = tiles_m * tiles_n;
 
-    // persistent CTA: items (m-tile, n-chunk) are walked with a one-chunk-deep software pipeline -- the A chunk of the
-    // NEXT (item, k-chunk) is already in flight (registers) while the current one is multiplied / its tile is stored,
-    // so small-K GEMMs (K <= 32: a single chunk per tile) are bandwidth- instead of latency-bound.
-    auto load_chunk = [&](int item, int kc, float4 (&v)[4]) {
-        const int64_t m0 = (int64_t)(item / tiles_n) * PW_BM;
-        const int k = kc + sk4 * 4;
+    int l_item = blockIdx.x, l_kc = 0;                   // load cursor (runs ahead of the compute cursor)
+    auto issue_load = [&](int stage) {
+        if (l_item < total) {
+            float* dst = As_all + (size_t)stage * (PW_BM * PW_LDA);
+            const int64_t m0 = (int64_t)(l_item / tiles_n) * PW_BM;
+            const int k = l_kc + sk4 * 4;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int64_t m = m0 + srow + 32 * i;
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m < p.M && k < K) {
-                x = __ldg(reinterpret_cast<const float4*>(p.A + m * K + k));
-                if (p.se_scale) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(p.se_scale + (m / p.hw) * K + k));
-                    x.x *= sc.x; x.y *= sc.y; x.z *= sc.z; x.w *= sc.w;
-                }
+            for (int i = 0; i < 4; i++) {
+                const int64_t m = m0 + srow + 32 * i;
+                const bool ok = (m < p.M) && (k < K);
+                cp_async16(dst + (srow + 32 * i) * PW_LDA + sk4 * 4, ok ? (const void*)(p.A + m * K + k) : (const void*)p.A, ok);
             }
-            v[i] = x;
+            l_kc += PW_KC;
+            if (l_kc >= K) { l_kc = 0; l_item += gridDim.x; }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    float4 stage[4];
-    int item = blockIdx.x;
-    if (item < total) load_chunk(item, 0, stage);
-    for (; item < total; item += gridDim.x) {
+#pragma unroll
+    for (int s = 0; s < PW_STAGES - 1; s++) issue_load(s);
+
+    int stage = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
         const int64_t m0 = (int64_t)(item / tiles_n) * PW_BM;
         const int nt0 = (item % tiles_n) * PW_NT, ntc = min(PW_NT, n8 - nt0);
+        const int64_t r[2] = {m0 + warp * 16 + g, m0 + warp * 16 + g + 8};
+        const float* sc0 = nullptr; const float* sc1 = nullptr;
+        if (p.se_scale) {
+            sc0 = p.se_scale + (min(r[0], p.M - 1) / p.hw) * K + t;
+            sc1 = p.se_scale + (min(r[1], p.M - 1) / p.hw) * K + t;
+        }
         float acc[PW_NT][4];
 #pragma unroll
         for (int j = 0; j < PW_NT; j++) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
         for (int kc = 0; kc < K; kc += PW_KC) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(As + (srow + 32 * i) * PW_LDA + sk4 * 4) = stage[i];
-            __syncthreads();
-            if (kc + PW_KC < K) load_chunk(item, kc + PW_KC, stage);
-            else if (item + (int)gridDim.x < total) load_chunk(item + gridDim.x, 0, stage);
+            asm volatile("cp.async.wait_group %0;" ::"n"(PW_STAGES - 2) : "memory");
+            __syncthreads();                              // chunk `stage` has landed; everyone is done with the slot refilled next
+            issue_load((stage + PW_STAGES - 1) % PW_STAGES);
+            const float* As = As_all + (size_t)stage * (PW_BM * PW_LDA);
             const int ksteps = min(PW_KC, K - kc) >> 3;
             const float* a0p = As + (warp * 16 + g) * PW_LDA + t;
             const float* a1p = a0p + 8 * PW_LDA;
             for (int ks = 0; ks < ksteps; ks++) {
-                const float av[4] = {a0p[ks * 8], a1p[ks * 8], a0p[ks * 8 + 4], a1p[ks * 8 + 4]};
+                float av[4] = {a0p[ks * 8], a1p[ks * 8], a0p[ks * 8 + 4], a1p[ks * 8 + 4]};
+                if (sc0) {
+                    const int k = kc + ks * 8;
+                    av[0] *= __ldg(sc0 + k); av[1] *= __ldg(sc1 + k); av[2] *= __ldg(sc0 + k + 4); av[3] *= __ldg(sc1 + k + 4);
+                }
                 uint32_t ah[4], al[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -93,10 +111,9 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
                     }
                 }
             }
-            __syncthreads();
+            stage = (stage + 1) % PW_STAGES;
         }
         // epilogue: rows r0 = g, r1 = g + 8 of this warp's 16-row slab; columns n = (nt0+j)*8 + 2t, +1
-        const int64_t r[2] = {m0 + warp * 16 + g, m0 + warp * 16 + g + 8};
         int64_t rbase[2] = {0, 0};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -125,14 +142,18 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s) {
     if ((p.K & 7) || (p.N & 7)) { set_error("pointwise_mma: K and N must be multiples of 8 (got %d, %d)", p.K, p.N); return KPD_ERR_UNSUPPORTED; }
     if (p.M <= 0) return 0;
     const int tiles_m = (int)((p.M + PW_BM - 1) / PW_BM), tiles_n = ((p.N >> 3) + PW_NT - 1) / PW_NT;
+    const size_t smem = sizeof(float) * PW_STAGES * PW_BM * PW_LDA;           // 72 KB: 2-3 CTAs per SM
+    static bool attr = false;
+    if (!attr) { KPD_CUDA(cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     const int grid = (int)std::min<int64_t>((int64_t)tiles_m * tiles_n, (int64_t)sm_count * 2);
-    pw_mma_kernel<<<grid, PW_THREADS, 0, s>>>(p, tiles_m, tiles_n);
+    pw_mma_kernel<<<grid, PW_THREADS, smem, s>>>(p, tiles_m, tiles_n);
     KPD_LAUNCH_CHECK();
     return 0;
 }

@@ -51,6 +51,7 @@ _SIGNATURES = {
                                C.POINTER(WorkspaceLayout), _P]),
     "kpd_roi_align": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "kpd_heatmap_head": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.POINTER(WorkspaceLayout), _P]),
+    "kpd_dense_conv": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "kpd_decode": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
                              _P, _P, _P, _P, _P, _P, _P, _P]),
     "kpd_person_heads": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P, _P]),

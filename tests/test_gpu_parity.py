@@ -381,3 +381,36 @@ def test_standalone_modules(model, sd):
     for a, b in zip(outs, refs):
         assert tuple(a.shape) == tuple(b.shape)
         assert rel_range_err(a.cpu().numpy(), b.numpy()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------- tensor-core conv variants
+@pytest.mark.parametrize("conv,n,hw", [(0, 2, 32), (0, 1, 112), (1, 3, 56), (2, 3, 56), (3, 2, 56), (3, 1, 40)])
+def test_dense_conv_variants_agree(model, conv, n, hw):
+    """kpd_dense_conv: classic tcgen05 (tf32 / bf16) and tap-reuse tcgen05 (chunk-major input) against the fp32 CUDA-core conv."""
+    import ctypes as C
+    from dll import _native as N
+    model.set_precision("fp32_strict")
+    plan, dev = model._plan()
+    cin = {0: 128, 1: 64, 2: 256, 3: 256}[conv]; cout = {0: 128, 1: 256, 2: 256, 3: 64}[conv]
+    g = torch.Generator(device="cuda").manual_seed(conv * 7 + hw)
+    x = torch.randn(n, hw, hw, cin, device="cuda", generator=g).clamp_min(-0.5)
+
+    def run(impl, inp, out_dtype):
+        out = torch.empty(n, hw, hw, cout, device="cuda", dtype=out_dtype)
+        N.check(N.load().kpd_dense_conv(plan.handle, conv, impl, N.ptr(inp), N.ptr(out), n, hw, hw, N.stream_ptr(dev)), "kpd_dense_conv")
+        torch.cuda.synchronize()
+        return out.float()
+
+    def chunk_major(t):
+        e = 16 // t.element_size()
+        return t.view(n, hw, hw, cin // e, e).permute(0, 3, 1, 2, 4).contiguous()
+    ref = run(0, x, torch.float32)
+    peak = float(ref.abs().max())
+    xb = x.to(torch.bfloat16)
+    errs = {"tf32": float((run(1, x, torch.float32) - ref).abs().max()) / peak,
+            "bf16": float((run(2, xb, torch.bfloat16) - ref).abs().max()) / peak,
+            "tf32_halo": float((run(3, chunk_major(x), torch.float32) - ref).abs().max()) / peak,
+            "bf16_halo": float((run(4, chunk_major(xb), torch.bfloat16) - ref).abs().max()) / peak}
+    _report(f"dense_conv/{conv}/{n}x{hw}", errs)
+    assert errs["tf32"] < 2e-3 and errs["tf32_halo"] < 2e-3, errs
+    assert errs["bf16"] < 2e-2 and errs["bf16_halo"] < 2e-2, errs
