@@ -146,13 +146,22 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     char* ws = static_cast<char*>(d_workspace);
     KPD_TRY(run_body(plan, d_images, B, S, precision == KPD_PREC_FP32_SIMT, ws, L, s));
     KPD_TRY(run_fpn_laterals(plan, B, S, precision != KPD_PREC_FP32_SIMT, precision == KPD_PREC_FP32_SIMT, ws, L, s));
+    const ScratchMap sm = scratch_map(B, S, 1);
+    float* pool_part = reinterpret_cast<float*>(ws + L.scratch + sm.pool_part);
+    const int H0 = S / 2;
+    const bool fuse_pool = precision != KPD_PREC_FP32_SIMT && (H0 % 16 == 0) && (H0 % 8 == 0);
     {
         ProfScope ps("fpn0_conv", s);
-        KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, S / 2, S / 2, 0, nullptr, s));
+        if (fuse_pool)      // avg/max pooling for the channel scores is reduced in the conv epilogue (fp32 accumulators)
+            KPD_TRY(conv_dense_umma(plan, plan->fpn_conv[0], 0, ws + L.lateral0, ws + L.fpn0, 0, B, H0, H0, ACT_RELU, 0, nullptr, s, pool_part));
+        else
+            KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, H0, H0, 0, nullptr, s));
     }
-    const ScratchMap sm = scratch_map(B, S, 1);
-    KPD_TRY(run_pools(reinterpret_cast<const float*>(ws + L.fpn0), B, (S / 2) * (S / 2), reinterpret_cast<float*>(ws + L.pool_avg),
-                      reinterpret_cast<float*>(ws + L.pool_max), reinterpret_cast<float*>(ws + L.scratch + sm.pool_part), s));
+    if (fuse_pool)
+        KPD_TRY(run_pool_final(pool_part, B, (H0 / 16) * (H0 / 8), H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg), reinterpret_cast<float*>(ws + L.pool_max), s));
+    else
+        KPD_TRY(run_pools(reinterpret_cast<const float*>(ws + L.fpn0), B, H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg),
+                          reinterpret_cast<float*>(ws + L.pool_max), pool_part, s));
     return 0;
 }
 

@@ -114,11 +114,13 @@ ScratchMap scratch_map(int B, int S, int n_rois);
 int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* scratch, cudaStream_t s);
+int run_pool_final(const float* partials, int B, int parts, int HW, float* avg, float* mx, cudaStream_t s);
 int run_scores_topk(const kpd_plan* p, int B, const float* avg, const float* mx, float* scores, int32_t* topk, cudaStream_t s);
 int conv_dense_simt(const DenseConv& c, const float* in, float* out, int N, int H, int W, int act,
                     const int32_t* n_valid, cudaStream_t s);
 int conv_dense_umma(const kpd_plan* p, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
-                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s);
+                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s,
+                    float* pool_part = nullptr);
 int pointwise(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
               int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s);
 }  // namespace kpd

@@ -89,6 +89,7 @@ struct ConvParams {
     int tw, th, tn;                    // pixel box of one 128-row tile: tw*th*tn == 128
     int tiles_w, tiles_h, tiles_n;
     int act, out_bf16, stages, round_out_tf32;
+    float* pool_part;                  // optional: per-tile channel sum/max partials [n][tiles_h*tiles_w][2][Cout] (tn must be 1)
     int out_cm;                        // 1: write [N][Cout/E16][H][W][E16] (16-byte channel chunks, the halo kernel's input layout)
     const float* bias;
     void* out;                         // NHWC [N,H,W,Cout], bf16 or fp32
@@ -152,6 +153,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
+    float* red = sbias + p.Cout;                      // pooling only: [4 warps][32][33] transpose tiles
+    float* wred = red + 4 * 32 * 33;                  // pooling only: [4 warps][2][Cout] per-warp channel sum / max
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -249,21 +252,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t r[32];
                 tc_ld32(taddr + c0, r);
                 tc_wait_ld();
-                if (valid) {
-                    float v[32];
+                float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        float x = __uint_as_float(r[j]) + sbias[c0 + j];
-                        x = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
-                        v[j] = p.round_out_tf32 ? tf32_rna(x) : x;
-                    }
-                    epi_store(p, v, n, h, w, pix, c0);
+                for (int j = 0; j < 32; j++) {
+                    float x = __uint_as_float(r[j]) + sbias[c0 + j];
+                    x = p.act == ACT_RELU ? fmaxf(x, 0.f) : x;
+                    v[j] = p.round_out_tf32 ? tf32_rna(x) : x;
+                }
+                if (valid) epi_store(p, v, n, h, w, pix, c0);
+                if (p.pool_part) {
+                    // fused global avg/max pooling (keypoint_model.py:37,40): per-warp transpose through shared memory so
+                    // that lane j reduces channel c0+j over this warp's 32 pixels, from the fp32 accumulators
+                    float* rt = red + lg * (32 * 33);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) rt[lane * 33 + j] = valid ? v[j] : 0.f;
+                    __syncwarp();
+                    float sm_ = 0.f, mx_ = -INFINITY;
+                    for (int rr = 0; rr < 32; rr++) { const float x = rt[rr * 33 + lane]; sm_ += x; mx_ = fmaxf(mx_, x); }
+                    wred[(lg * 2 + 0) * p.Cout + c0 + lane] = sm_;
+                    wred[(lg * 2 + 1) * p.Cout + c0 + lane] = mx_;
+                    __syncwarp();
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (p.pool_part) {                       // combine the 4 epilogue warps (named barrier 1, 128 threads)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int et = (warp - 2) * 32 + lane;
+                float* dst = p.pool_part + ((size_t)in * (p.tiles_h * p.tiles_w) + (tile - in * (p.tiles_h * p.tiles_w))) * 2 * p.Cout;
+                for (int c = et; c < p.Cout; c += 128) {
+                    dst[c] = (wred[0 * p.Cout + c] + wred[2 * p.Cout + c]) + (wred[4 * p.Cout + c] + wred[6 * p.Cout + c]);
+                    dst[p.Cout + c] = fmaxf(fmaxf(wred[1 * p.Cout + c], wred[3 * p.Cout + c]), fmaxf(wred[5 * p.Cout + c], wred[7 * p.Cout + c]));
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
         }
     }
     tc_fence_before();
@@ -446,7 +470,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
-                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s) {
+                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s, float* pool_part) {
     if (N <= 0) return 0;
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
@@ -458,8 +482,10 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     if (W % 16 == 0 && H % 8 == 0) { p.tw = 16; p.th = 8; p.tn = 1; } else { p.tw = 8; p.th = 8; p.tn = 2; }
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
     p.act = act; p.round_out_tf32 = round_out_tf32; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
+    p.pool_part = pool_part;
+    if (pool_part && p.tn != 1) { set_error("conv_dense_umma: fused pooling needs W %% 16 == 0 and H %% 8 == 0"); return KPD_ERR_UNSUPPORTED; }
     const int stage_bytes = A_BYTES + c.cout * 128;
-    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64;
+    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0);
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
     p.stages = stages;

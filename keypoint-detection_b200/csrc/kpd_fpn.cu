@@ -30,11 +30,11 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(128) pool_final_kernel(const float* __restrict__ part, float* __restrict__ avg,
-                                                         float* __restrict__ mx, int HW) {
+                                                         float* __restrict__ mx, int HW, int parts) {
     const int b = blockIdx.x, c = threadIdx.x;
     float s = 0.f, m = -INFINITY;
-    for (int i = 0; i < POOL_PARTS; i++) {
-        const float* o = part + (((int64_t)b * POOL_PARTS + i) * 2) * 128;
+    for (int i = 0; i < parts; i++) {
+        const float* o = part + (((int64_t)b * parts + i) * 2) * 128;
         s += o[c]; m = fmaxf(m, o[128 + c]);
     }
     avg[(int64_t)b * 128 + c] = s / (float)HW;
@@ -45,7 +45,15 @@ int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* sc
     ProfScope ps("pool", s);
     pool_partial_kernel<<<dim3(POOL_PARTS, B), 256, 0, s>>>(fpn0, scratch, HW);
     KPD_LAUNCH_CHECK();
-    pool_final_kernel<<<B, 128, 0, s>>>(scratch, avg, mx, HW);
+    pool_final_kernel<<<B, 128, 0, s>>>(scratch, avg, mx, HW, POOL_PARTS);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+// second level of the pooling fused into the FPN-0 conv epilogue: `parts` per-tile partials per image
+int run_pool_final(const float* partials, int B, int parts, int HW, float* avg, float* mx, cudaStream_t s) {
+    ProfScope ps("pool", s);
+    pool_final_kernel<<<B, 128, 0, s>>>(partials, avg, mx, HW, parts);
     KPD_LAUNCH_CHECK();
     return 0;
 }

@@ -71,27 +71,30 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
     for (int q = warp; q < 2 * 56; q += 8) {
         const int ph = row0 + q / 56, pw = q % 56;
         float a0 = 0.f, a1 = 0.f;
-        for (int iy = 0; iy < gh; iy++) {
+        auto sample = [&](int iy, int ix) {
             float y = y1 + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)gh;
-            const bool yok = !(y < -1.f || y > (float)H);
-            y = fmaxf(y, 0.f);
-            int yl = (int)y, yh;
+            float x = x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw;
+            if (y < -1.f || y > (float)H || x < -1.f || x > (float)W) return;
+            y = fmaxf(y, 0.f); x = fmaxf(x, 0.f);
+            int yl = (int)y, yh, xl = (int)x, xh;
             if (yl >= H - 1) { yl = yh = H - 1; y = (float)yl; } else yh = yl + 1;
-            const float ly = y - (float)yl, hy = 1.f - ly;
-            for (int ix = 0; ix < gw; ix++) {
-                float x = x1 + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)gw;
-                const bool ok = yok && !(x < -1.f || x > (float)W);
-                x = fmaxf(x, 0.f);
-                int xl = (int)x, xh;
-                if (xl >= W - 1) { xl = xh = W - 1; x = (float)xl; } else xh = xl + 1;
-                const float lx = x - (float)xl, hx = 1.f - lx;
-                if (!ok) continue;
-                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                const float* p1 = fb + ((int64_t)yl * W + xl) * 128; const float* p2 = fb + ((int64_t)yl * W + xh) * 128;
-                const float* p3 = fb + ((int64_t)yh * W + xl) * 128; const float* p4 = fb + ((int64_t)yh * W + xh) * 128;
-                a0 += w1 * __ldg(p1 + c0) + w2 * __ldg(p2 + c0) + w3 * __ldg(p3 + c0) + w4 * __ldg(p4 + c0);
-                a1 += w1 * __ldg(p1 + c1) + w2 * __ldg(p2 + c1) + w3 * __ldg(p3 + c1) + w4 * __ldg(p4 + c1);
-            }
+            if (xl >= W - 1) { xl = xh = W - 1; x = (float)xl; } else xh = xl + 1;
+            const float ly = y - (float)yl, hy = 1.f - ly, lx = x - (float)xl, hx = 1.f - lx;
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const float* p1 = fb + ((int64_t)yl * W + xl) * 128; const float* p2 = fb + ((int64_t)yl * W + xh) * 128;
+            const float* p3 = fb + ((int64_t)yh * W + xl) * 128; const float* p4 = fb + ((int64_t)yh * W + xh) * 128;
+            a0 += w1 * __ldg(p1 + c0) + w2 * __ldg(p2 + c0) + w3 * __ldg(p3 + c0) + w4 * __ldg(p4 + c0);
+            a1 += w1 * __ldg(p1 + c1) + w2 * __ldg(p2 + c1) + w3 * __ldg(p3 + c1) + w4 * __ldg(p4 + c1);
+        };
+        if (gh <= 2 && gw <= 2) {          // S=224 (ROI <= 112 px): fully unrolled so all 32 gathers of a pixel are in flight
+#pragma unroll
+            for (int iy = 0; iy < 2; iy++)
+#pragma unroll
+                for (int ix = 0; ix < 2; ix++)
+                    if (iy < gh && ix < gw) sample(iy, ix);
+        } else {
+            for (int iy = 0; iy < gh; iy++)
+                for (int ix = 0; ix < gw; ix++) sample(iy, ix);
         }
         a0 /= count; a1 /= count;
         float* o = roi_feat + (((int64_t)n * 56 + ph) * 56 + pw) * 64;
