@@ -419,12 +419,22 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
         KPD_TRY(pointwise_mma(a, p->sm_count, s));
     }
-    if (!strict_fp32) {                                 // lateral 0 (K=16): dedicated streaming kernel (512 B/pixel out)
-        const int64_t pixels = (int64_t)B * hs[0] * hs[0];
-        const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)p->sm_count * 8);
-        lateral0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0],
-                                             pixels, hs[0], hs[0], hs[0] / hs[1], round_tf32);
-        KPD_LAUNCH_CHECK();
+    if (!strict_fp32) {
+        // lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add: CUDA-core streaming kernel (exact fp32, then rounded to tf32
+        // for the FPN-0 MMA).  KPD_LATERAL0_UMMA=1 selects the tcgen05 variant (kind::tf32, 64-byte swizzled K rows, residual
+        // added in the epilogue): measured no faster (its row-per-thread fp32 epilogue stores 512 B/pixel in 16-byte pieces)
+        // and its single-pass tf32 inputs cost score accuracy (1.2e-5 vs 3e-6), so it is not the default.
+        static const bool umma = getenv("KPD_LATERAL0_UMMA") != nullptr;
+        if (umma && hs[0] % 16 == 0) {
+            KPD_TRY(conv_dense_umma(p, p->lat0_conv, 0, ws + L.feat[0], lat[0], 0, B, hs[0], hs[0], ACT_NONE, round_tf32, nullptr, s,
+                                    nullptr, lat[1], hs[0] / hs[1]));
+        } else {
+            const int64_t pixels = (int64_t)B * hs[0] * hs[0];
+            const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)p->sm_count * 8);
+            lateral0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0],
+                                                 pixels, hs[0], hs[0], hs[0] / hs[1], round_tf32);
+            KPD_LAUNCH_CHECK();
+        }
     }
     if (!strict_fp32) return 0;
     for (int i = 3; i >= 0; i--) {

@@ -92,6 +92,7 @@ struct kpd_plan {
     // fpn
     const float* w_lat[4];                        // [cin_i][128]
     const float4* wf_lat[4];                      // laterals as 3xTF32 mma fragments
+    kpd::DenseConv lat0_conv;                     // lateral 0 (1x1, 16 -> 128) packed for the tcgen05 kernel (64-byte K rows)
     kpd::DenseConv fpn_conv[4];
     // channel attention (model level): fc0 [8][128]+[8], fc2 [128][8]+[128]
     const float *ca_w0, *ca_b0, *ca_w2, *ca_b2;
@@ -120,7 +121,7 @@ int conv_dense_simt(const DenseConv& c, const float* in, float* out, int N, int 
                     const int32_t* n_valid, cudaStream_t s);
 int conv_dense_umma(const kpd_plan* p, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
                     int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s,
-                    float* pool_part = nullptr);
+                    float* pool_part = nullptr, const float* res = nullptr, int res_up = 1);
 int pointwise(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
               int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s);
 }  // namespace kpd

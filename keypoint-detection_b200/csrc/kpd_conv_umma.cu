@@ -83,12 +83,19 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// same for K slabs of `row_bytes` = 128 (SWIZZLE_128B, layout 2) or 64 (SWIZZLE_64B, layout 4): SBO = 8 rows * row_bytes
+__device__ __forceinline__ uint64_t make_sdesc_rb(uint32_t saddr, int row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * row_bytes) >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
 
 struct ConvParams {
     int N, H, W, Cin, Cout, taps;      // N = allocated instances (tensor-map extent)
     int tw, th, tn;                    // pixel box of one 128-row tile: tw*th*tn == 128
     int tiles_w, tiles_h, tiles_n;
     int act, out_bf16, stages, round_out_tf32;
+    int row_bytes;                     // bytes of K per shared-memory row: 128 (default) or 64 (Cin*elt == 64, e.g. the 16-ch fp32 lateral)
+    const float* res; int res_up;      // optional residual added in the epilogue: nearest-upsampled [N][H/up][W/up][Cout] fp32 (FPN top-down)
     float* pool_part;                  // optional: per-tile channel sum/max partials [n][tiles_h*tiles_w][2][Cout] (tn must be 1)
     int out_cm;                        // 1: write [N][Cout/E16][H][W][E16] (16-byte channel chunks, the halo kernel's input layout)
     const float* bias;
@@ -139,7 +146,6 @@ __device__ __forceinline__ void epi_store(const ConvParams& p, const float (&v)[
 }
 
 constexpr int UMMA_THREADS = 192;
-constexpr int A_BYTES = 128 * 128;     // 128 rows x 128 bytes
 
 template <bool BF16>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
@@ -147,7 +153,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A | B)] | barriers | tmem slot | bias
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int B_BYTES = p.Cout * 128;
+    const int RB = p.row_bytes;
+    const int A_BYTES = 128 * RB, B_BYTES = p.Cout * RB;
     const int STAGE_BYTES = A_BYTES + B_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
@@ -186,9 +193,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_live = p.n_valid ? min(*p.n_valid, p.N) : p.N;
     const int tiles_n_live = (n_live + p.tn - 1) / p.tn;
     const int total_tiles = tiles_n_live * p.tiles_h * p.tiles_w;
-    constexpr int BK = BF16 ? 64 : 32;                 // elements per 128-byte K slab
+    const int BK = RB / (BF16 ? 2 : 4);                // elements per K slab (one swizzled row)
     const int cchunks = p.Cin / BK;
     const int kiters = p.taps * cchunks;
+    const int ksteps = RB / 32;                        // MMAs per slab (32 bytes of K each)
     const int ksz = p.taps == 9 ? 3 : 1, pad = p.taps == 9 ? 1 : 0;
 
     if (warp == 0) {
@@ -224,9 +232,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A_BYTES);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++)      // 4 x 32-byte K steps inside the 128-byte swizzle row
+                    const uint64_t adesc = make_sdesc_rb(sa, RB), bdesc = make_sdesc_rb(sa + A_BYTES, RB);
+                    for (int k4 = 0; k4 < ksteps; k4++) // 32-byte K steps inside the swizzled row
                         tc_mma<BF16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
                     tc_commit(empty_bar(stage));        // frees this smem stage once the MMAs above retire
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -253,6 +260,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_ld32(taddr + c0, r);
                 tc_wait_ld();
                 float v[32];
+                if (p.res && valid) {                 // + nearest-upsampled coarser lateral (backbone.py:35-37)
+                    const float4* rp = reinterpret_cast<const float4*>(
+                        p.res + (((size_t)n * (p.H / p.res_up) + h / p.res_up) * (p.W / p.res_up) + w / p.res_up) * p.Cout + c0);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 t4 = __ldg(rp + q);
+                        r[4 * q + 0] = __float_as_uint(__uint_as_float(r[4 * q + 0]) + t4.x); r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + t4.y);
+                        r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + t4.z); r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + t4.w);
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
                     float x = __uint_as_float(r[j]) + sbias[c0 + j];
@@ -470,21 +487,23 @@ static EncodeTiledFn get_encode() {
 }
 
 int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
-                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s, float* pool_part) {
+                    int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s, float* pool_part,
+                    const float* res, int res_up) {
     if (N <= 0) return 0;
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
     const int elt = prec_bf16 ? 2 : 4;
-    const int BK = 128 / elt;
+    const int row_bytes = (c.cin * elt) % 128 == 0 ? 128 : 64;      // 64-byte swizzle for the 16-channel fp32 lateral
+    const int BK = row_bytes / elt;
     if (c.cin % BK != 0 || c.cout % 16 != 0 || c.cout > 256 || c.cout < 16) { set_error("conv_dense_umma: unsupported channels %d->%d", c.cin, c.cout); return KPD_ERR_UNSUPPORTED; }
     ConvParams p{};
     p.N = N; p.H = H; p.W = W; p.Cin = c.cin; p.Cout = c.cout; p.taps = c.taps;
     if (W % 16 == 0 && H % 8 == 0) { p.tw = 16; p.th = 8; p.tn = 1; } else { p.tw = 8; p.th = 8; p.tn = 2; }
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
     p.act = act; p.round_out_tf32 = round_out_tf32; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
-    p.pool_part = pool_part;
+    p.pool_part = pool_part; p.row_bytes = row_bytes; p.res = res; p.res_up = res_up > 0 ? res_up : 1;
     if (pool_part && p.tn != 1) { set_error("conv_dense_umma: fused pooling needs W %% 16 == 0 and H %% 8 == 0"); return KPD_ERR_UNSUPPORTED; }
-    const int stage_bytes = A_BYTES + c.cout * 128;
+    const int stage_bytes = 128 * row_bytes + c.cout * row_bytes;
     const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0);
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
@@ -498,7 +517,7 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tn};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tmA, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
-                         const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         const_cast<void*>(in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return KPD_ERR_STATE; }
     }
@@ -510,7 +529,7 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         cuuint32_t es[2] = {1, 1};
         const void* wptr = prec_bf16 ? static_cast<const void*>(c.w_bf16) : static_cast<const void*>(c.w_tf32);
         CUresult r = enc(&tmB, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
-                         const_cast<void*>(wptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         const_cast<void*>(wptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return KPD_ERR_STATE; }
     }

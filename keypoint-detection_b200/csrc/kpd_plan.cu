@@ -253,8 +253,10 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         reg(&p->wf_last, pack_mma_frag(B, ow, 96, 576));
     }
     const int fpn_in[4] = {16, 24, 48, 576};
+    const float* w_lat0_raw = nullptr;
     for (int i = 0; i < 4; i++) {
         const float* w = c.next();
+        if (i == 0) w_lat0_raw = w;
         pack_conv_kc(B, w, nullptr, nullptr, 0, 128, fpn_in[i], 1, ow, ob);
         reg(&p->w_lat[i], ow);
         reg(&p->wf_lat[i], pack_mma_frag(B, ow, fpn_in[i], 128));
@@ -264,6 +266,7 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         d.cin = cin; d.cout = cout; d.taps = k * k;
         reg(&d.w_simt, off[0]); reg(&d.w_tf32, off[1]); reg(&d.w_bf16, off[2]); reg(&d.bias, off[3]);
     };
+    dense(p->lat0_conv, w_lat0_raw, nullptr, nullptr, 0, 128, 16, 1);
     for (int i = 0; i < 4; i++) {
         const float* w = c.next(); BN bn = read_bn(c);
         dense(p->fpn_conv[i], w, nullptr, &bn, EPS_HEAD, 128, 128, 3);
