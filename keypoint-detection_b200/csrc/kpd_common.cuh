@@ -28,6 +28,17 @@ void prof_end(cudaStream_t s);
         return (int)_e; } } while (0)
 #define KPD_TRY(expr) do { int _r = (expr); if (_r != 0) return _r; } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember which devices a kernel was configured on.
+template <typename F>
+inline cudaError_t ensure_smem_attr(F func, int bytes, uint64_t& done_mask) {
+    int dev = 0; cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 64 && (done_mask >> dev) & 1ull) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev < 64) done_mask |= 1ull << dev;
+    return e;
+}
+
 struct ProfScope {
     cudaStream_t s;
     ProfScope(const char* tag, cudaStream_t st) : s(st) { prof_begin(tag, s); }

@@ -423,12 +423,9 @@ int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out,
     a.p_exp = m.w_exp ? pick_p(std::min(a.chunk_rows, (a.rows_per_cta - 1) * m.stride + m.k) * H, m.exp / 4) : 1;
     a.p_proj = pick_p(a.rows_per_cta * a.Ho, m.cout / 4);
     const size_t bytes = sizeof(float) * (size_t)a.smem_floats;
-    static bool attr_set = false;
-    if (!attr_set) {
-        KPD_CUDA(cudaFuncSetAttribute(mbconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        KPD_CUDA(cudaFuncSetAttribute(mbconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    static uint64_t attr_t = 0, attr_f = 0;
+    KPD_CUDA(ensure_smem_attr(mbconv_kernel<true>, 200 * 1024, attr_t));
+    KPD_CUDA(ensure_smem_attr(mbconv_kernel<false>, 200 * 1024, attr_f));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(B * C)); cfg.blockDim = dim3(MB_THREADS); cfg.dynamicSmemBytes = bytes; cfg.stream = s;
     cudaLaunchAttribute attr[1];

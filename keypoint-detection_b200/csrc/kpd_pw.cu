@@ -150,8 +150,8 @@ int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s) {
     if (p.M <= 0) return 0;
     const int tiles_m = (int)((p.M + PW_BM - 1) / PW_BM), tiles_n = ((p.N >> 3) + PW_NT - 1) / PW_NT;
     const size_t smem = sizeof(float) * PW_STAGES * PW_BM * PW_LDA;           // 72 KB: 2-3 CTAs per SM
-    static bool attr = false;
-    if (!attr) { KPD_CUDA(cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static uint64_t attr_mask = 0;
+    KPD_CUDA(ensure_smem_attr(pw_mma_kernel, (int)smem, attr_mask));
     const int grid = (int)std::min<int64_t>((int64_t)tiles_m * tiles_n, (int64_t)sm_count * 2);
     pw_mma_kernel<<<grid, PW_THREADS, smem, s>>>(p, tiles_m, tiles_n);
     KPD_LAUNCH_CHECK();
@@ -282,12 +282,9 @@ int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool
     const size_t smem = sizeof(float) * ((size_t)((TH - 1) * m.stride + m.k) * ((TW - 1) * m.stride + m.k) * CG + (size_t)m.k * m.k * CG + CG);
     dim3 grid(tiles_x * tiles_y, (C + CG - 1) / CG, B);
     (void)sm_count;
-    static bool attr = false;
-    if (!attr) {
-        KPD_CUDA(cudaFuncSetAttribute(dw_tiled_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        KPD_CUDA(cudaFuncSetAttribute(dw_tiled_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
-    }
+    static uint64_t attr3 = 0, attr5 = 0;
+    KPD_CUDA(ensure_smem_attr(dw_tiled_kernel<3>, 64 * 1024, attr3));
+    KPD_CUDA(ensure_smem_attr(dw_tiled_kernel<5>, 64 * 1024, attr5));
     if (m.k == 3) dw_tiled_kernel<3><<<grid, 256, smem, s>>>(in, m.w_dw, m.b_dw, out, pool, H, C, m.stride, m.act, TH, TW, tiles_x, CG);
     else          dw_tiled_kernel<5><<<grid, 256, smem, s>>>(in, m.w_dw, m.b_dw, out, pool, H, C, m.stride, m.act, TH, TW, tiles_x, CG);
     KPD_LAUNCH_CHECK();

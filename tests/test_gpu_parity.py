@@ -414,3 +414,24 @@ def test_dense_conv_variants_agree(model, conv, n, hw):
     _report(f"dense_conv/{conv}/{n}x{hw}", errs)
     assert errs["tf32"] < 2e-3 and errs["tf32_halo"] < 2e-3, errs
     assert errs["bf16"] < 2e-2 and errs["bf16_halo"] < 2e-2, errs
+
+
+def test_rgb_input_three_channels():
+    """in_channels=3 (BackboneConfig default): stem conv over an NCHW RGB image, strict mode vs the oracle."""
+    from dll import MultiPersonKeypointModel
+    from dll.configs import ModelConfig, BackboneConfig, TrainingConfig
+    from dll.configs.model_config import HeatmapHeadConfig
+    cfg = ModelConfig(backbone=BackboneConfig(in_channels=3), heatmap_head=HeatmapHeadConfig(heatmap_size=(56, 56)))
+    sd3 = synth_state_dict(seed=0, in_channels=3, style="stock")
+    m = MultiPersonKeypointModel(cfg, TrainingConfig(), precision="fp32_strict")
+    m.load_state_dict(sd3, strict=True)
+    m = m.cuda().eval()
+    x = torch.from_numpy(synth_images(1, 3, 224, seed=5))
+    b = torch.from_numpy(synth_boxes(1, 2, seed=3))
+    ref = OM.forward(sd3, x, b, return_stages=True)
+    out = m.predict({"image": x, "bboxes": b}, topk_override=ref["stages"]["topk"].to(torch.int32))
+    e = rel_range_err(nchw(m.stage_tensors()["feat0"]), ref["stages"]["feats"][0].numpy())
+    assert e < 2e-5, e
+    hm, r = out["heatmap"].cpu().numpy(), ref["heatmap"].numpy()
+    assert float((np.abs(hm - r) / r).max()) < 1e-4
+    np.testing.assert_allclose(out["keypoints"].cpu().numpy(), ref["keypoints"].numpy(), atol=1e-5)
