@@ -15,6 +15,7 @@
 //     warps 2-5 epilogue (tcgen05.ld -> +bias -> ReLU -> bf16/fp32 NHWC stores).
 #include "kpd_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace kpd {
 
@@ -42,6 +43,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > 40000000u) { printf("kpd: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
+}
+// Epilogue-side wait: one lane polls with back-off so the idle epilogue warps do not steal issue slots from the
+// single-thread TMA producer / MMA issuer that share their SM sub-partitions; the rest of the warp parks at __syncwarp.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+    if (lane == 0) {
+        uint32_t spins = 0;
+        while (!mbar_try_wait(bar, parity)) {
+            __nanosleep(128);
+            if (++spins > 20000000u) { printf("kpd: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+        }
+    }
+    __syncwarp();
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -94,6 +107,7 @@ struct ConvParams {
     int tw, th, tn;                    // pixel box of one 128-row tile: tw*th*tn == 128
     int tiles_w, tiles_h, tiles_n;
     int act, out_bf16, stages, round_out_tf32;
+    int mt;                            // M-tiles (128 pixels each) that share one weight stage: 1, 2 or 4 (2*mt*Cout <= 512 TMEM columns)
     int row_bytes;                     // bytes of K per shared-memory row: 128 (default) or 64 (Cin*elt == 64, e.g. the 16-ch fp32 lateral)
     const float* res; int res_up;      // optional residual added in the epilogue: nearest-upsampled [N][H/up][W/up][Cout] fp32 (FPN top-down)
     float* pool_part;                  // optional: per-tile channel sum/max partials [n][tiles_h*tiles_w][2][Cout] (tn must be 1)
@@ -147,15 +161,18 @@ __device__ __forceinline__ void epi_store(const ConvParams& p, const float (&v)[
 
 constexpr int UMMA_THREADS = 192;
 
-template <bool BF16>
+// MT = M-tiles (128 pixels each) sharing one weight stage, RB = bytes of K per shared-memory row (128, or 64 for the
+// 16-channel fp32 lateral); both compile-time so that the single MMA-issuing thread runs a fully unrolled, lean loop
+// (its per-instruction overhead directly limits tensor throughput).
+template <bool BF16, int MT, int RB>
 __global__ void __launch_bounds__(UMMA_THREADS, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A | B)] | barriers | tmem slot | bias
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int RB = p.row_bytes;
-    const int A_BYTES = 128 * RB, B_BYTES = p.Cout * RB;
-    const int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int A_BYTES = 128 * RB;
+    const int B_BYTES = p.Cout * RB;
+    const int STAGE_BYTES = MT * A_BYTES + B_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
@@ -171,7 +188,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * S + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * S + 2 + a); };
 
-    int tmem_cols = 32; while (tmem_cols < 2 * p.Cout) tmem_cols <<= 1;
+    int tmem_cols = 32; while (tmem_cols < 2 * MT * p.Cout) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -193,26 +210,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_live = p.n_valid ? min(*p.n_valid, p.N) : p.N;
     const int tiles_n_live = (n_live + p.tn - 1) / p.tn;
     const int total_tiles = tiles_n_live * p.tiles_h * p.tiles_w;
-    const int BK = RB / (BF16 ? 2 : 4);                // elements per K slab (one swizzled row)
+    const int total_groups = (total_tiles + MT - 1) / MT;      // MT consecutive tiles share every weight stage
+    constexpr int BK = RB / (BF16 ? 2 : 4);            // elements per K slab (one swizzled row)
     const int cchunks = p.Cin / BK;
     const int kiters = p.taps * cchunks;
-    const int ksteps = RB / 32;                        // MMAs per slab (32 bytes of K each)
+    constexpr int ksteps = RB / 32;                    // MMAs per slab (32 bytes of K each)
     const int ksz = p.taps == 9 ? 3 : 1, pad = p.taps == 9 ? 1 : 0;
 
     if (warp == 0) {
         if (lane == 0) {                                // ---------------- TMA producer
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
-                const int w0 = iw * p.tw, h0 = ih * p.th, n0 = in * p.tn;
+            for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+                int w0[MT], h0[MT], n0[MT];             // tile origins: decoded once per group, not per K step
+#pragma unroll
+                for (int i = 0; i < MT; i++) {
+                    const int tile = min(grp * MT + i, total_tiles - 1);         // a short last group repeats its last tile
+                    const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
+                    w0[i] = iw * p.tw; h0[i] = ih * p.th; n0[i] = in * p.tn;
+                }
+                int tap = 0, cc = 0, dy = -pad, dx = -pad;
                 for (int kk = 0; kk < kiters; kk++) {
-                    const int tap = kk / cchunks, cc = kk - tap * cchunks;
-                    const int dy = tap / ksz - pad, dx = tap % ksz - pad;
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_expect_tx(full_bar(stage), (uint32_t)STAGE_BYTES);
                     const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    tma_load_4d(sa, &tmA, full_bar(stage), cc * BK, w0 + dx, h0 + dy, n0);
-                    tma_load_2d(sa + A_BYTES, &tmB, full_bar(stage), tap * p.Cin + cc * BK, 0);
+#pragma unroll
+                    for (int i = 0; i < MT; i++)
+                        tma_load_4d(sa + i * A_BYTES, &tmA, full_bar(stage), cc * BK, w0[i] + dx, h0[i] + dy, n0[i]);
+                    tma_load_2d(sa + MT * A_BYTES, &tmB, full_bar(stage), tap * p.Cin + cc * BK, 0);
+                    if (++cc == cchunks) { cc = 0; tap++; if (++dx == ksz - pad) { dx = -pad; dy++; } }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
@@ -224,17 +249,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t fmt = BF16 ? 1u : 2u;
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Cout);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * p.Cout);
                 for (int kk = 0; kk < kiters; kk++) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t adesc = make_sdesc_rb(sa, RB), bdesc = make_sdesc_rb(sa + A_BYTES, RB);
-                    for (int k4 = 0; k4 < ksteps; k4++) // 32-byte K steps inside the swizzled row
-                        tc_mma<BF16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
+                    const uint64_t bdesc = make_sdesc_rb(sa + MT * A_BYTES, RB);
+#pragma unroll
+                    for (int i = 0; i < MT; i++) {
+                        const uint64_t adesc = make_sdesc_rb(sa + i * A_BYTES, RB);
+#pragma unroll
+                        for (int k4 = 0; k4 < ksteps; k4++) // 32-byte K steps inside the swizzled row
+                            tc_mma<BF16>(d_tmem + (uint32_t)(i * p.Cout), adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
+                    }
                     tc_commit(empty_bar(stage));        // frees this smem stage once the MMAs above retire
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -247,14 +277,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = lg * 32 + lane;
         const int rw = row % p.tw, rh = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+          mbar_wait_warp(tfull_bar(acc), acc_phase, lane);
+          tc_fence_after();
+          for (int ti = 0; ti < MT; ti++) {
+            const int tile = grp * MT + ti;
+            if (tile >= total_tiles) break;
             const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
             const int w = iw * p.tw + rw, h = ih * p.th + rh, n = in * p.tn + rn;
             const bool valid = (w < p.W) && (h < p.H) && (n < n_live);
             const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.Cout);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((acc * MT + ti) * p.Cout);
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
                 uint32_t r[32];
                 tc_ld32(taddr + c0, r);
@@ -291,10 +324,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     __syncwarp();
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if (p.pool_part) {                       // combine the 4 epilogue warps (named barrier 1, 128 threads)
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int et = (warp - 2) * 32 + lane;
@@ -305,6 +334,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -439,7 +473,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int w = iw * 8 + rw, h = ih * 16 + rh;
             const bool valid = (w < p.W) && (h < p.H);
             const size_t pix = ((size_t)n * p.H + h) * p.W + w;
-            mbar_wait(tfull(acc), acc_phase);
+            mbar_wait_warp(tfull(acc), acc_phase, lane);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.Cout);
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
@@ -502,8 +536,14 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
     p.act = act; p.round_out_tf32 = round_out_tf32; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
     p.pool_part = pool_part; p.row_bytes = row_bytes; p.res = res; p.res_up = res_up > 0 ? res_up : 1;
+    static const int mt_env = getenv("KPD_CONV_MT") ? atoi(getenv("KPD_CONV_MT")) : 0;
+    int mt = 1;                                          // M-tiles per weight stage: as many as TMEM (512 columns, double-buffered) allows, <= 4
+    while (mt < 4 && 2 * (mt * 2) * c.cout <= 512) mt *= 2;
+    if (mt_env > 0) mt = std::min(mt, mt_env);
+    if (row_bytes == 64) mt = 1;
+    p.mt = mt;
     if (pool_part && p.tn != 1) { set_error("conv_dense_umma: fused pooling needs W %% 16 == 0 and H %% 8 == 0"); return KPD_ERR_UNSUPPORTED; }
-    const int stage_bytes = 128 * row_bytes + c.cout * row_bytes;
+    const int stage_bytes = mt * 128 * row_bytes + c.cout * row_bytes;
     const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0);
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
@@ -534,14 +574,21 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return KPD_ERR_STATE; }
     }
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
-    const int grid = std::min(total_tiles, plan->sm_count);
-    if (prec_bf16) {
-        KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_umma_kernel<true><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);
+    const int grid = std::min((total_tiles + mt - 1) / mt, plan->sm_count);
+#define KPD_LAUNCH_UMMA(BF, MTV, RBV)                                                                                     \
+    do {                                                                                                                  \
+        KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BF, MTV, RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv_umma_kernel<BF, MTV, RBV><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);                                     \
+    } while (0)
+    if (row_bytes == 64) {
+        if (prec_bf16 || mt != 1) { set_error("conv_dense_umma: 64-byte K rows are built for tf32, mt=1"); return KPD_ERR_UNSUPPORTED; }
+        KPD_LAUNCH_UMMA(false, 1, 64);
+    } else if (prec_bf16) {
+        if (mt == 4) KPD_LAUNCH_UMMA(true, 4, 128); else if (mt == 2) KPD_LAUNCH_UMMA(true, 2, 128); else KPD_LAUNCH_UMMA(true, 1, 128);
     } else {
-        KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        conv_umma_kernel<false><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);
+        if (mt == 4) KPD_LAUNCH_UMMA(false, 4, 128); else if (mt == 2) KPD_LAUNCH_UMMA(false, 2, 128); else KPD_LAUNCH_UMMA(false, 1, 128);
     }
+#undef KPD_LAUNCH_UMMA
     KPD_LAUNCH_CHECK();
     return 0;
 }
