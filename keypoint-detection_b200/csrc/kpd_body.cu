@@ -210,35 +210,81 @@ __global__ void __launch_bounds__(256) dw_kernel(const float* __restrict__ in, c
     }
 }
 
-// SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 ).  one block per image.
+// SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 ).
+// One CTA per SE_IMG images (the weight matrices are read once per CTA, not once per image: at C = 576 they are 2 x 332 KB,
+// and one-image CTAs made the layer L2-bandwidth bound).  Each layer is spread over (4-output group, k-slice) threads with
+// float4 weight loads, 8 in flight per thread, so enough bytes are outstanding to cover the L2 latency; the k-slices are
+// combined in a fixed order through shared memory (deterministic).
+constexpr int SE_IMG = 4, SE_MAXC = 576, SE_MAXSQ = 144, SE_SLICES = 8;
+constexpr int SE_PART = 4608;                             // floats: max over the layers of slices * SE_IMG * N (7*4*144 = 4032 at 576 -> 144)
+
+__device__ __forceinline__ int se_fc_partial(const float* __restrict__ W, const float* v, int K, int N, float* part) {
+    const int G = N >> 2;
+    int slices = min(min(SE_SLICES, (int)blockDim.x / G), K);
+    while (slices * SE_IMG * N > SE_PART) slices--;
+    const int tid = threadIdx.x;
+    if (tid < G * slices) {
+        const int g = tid % G, sl = tid / G;
+        const int per = (K + slices - 1) / slices, k0 = sl * per, k1 = min(K, k0 + per);
+        float4 acc[SE_IMG];
+#pragma unroll
+        for (int i = 0; i < SE_IMG; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* wp = reinterpret_cast<const float4*>(W) + g;
+        const int n4 = N >> 2;
+#pragma unroll 8
+        for (int k = k0; k < k1; k++) {
+            const float4 w = __ldg(wp + (size_t)k * n4);
+            const float4 x = *reinterpret_cast<const float4*>(v + k * SE_IMG);     // the SE_IMG images' k-th input
+            acc[0].x = fmaf(x.x, w.x, acc[0].x); acc[0].y = fmaf(x.x, w.y, acc[0].y); acc[0].z = fmaf(x.x, w.z, acc[0].z); acc[0].w = fmaf(x.x, w.w, acc[0].w);
+            acc[1].x = fmaf(x.y, w.x, acc[1].x); acc[1].y = fmaf(x.y, w.y, acc[1].y); acc[1].z = fmaf(x.y, w.z, acc[1].z); acc[1].w = fmaf(x.y, w.w, acc[1].w);
+            acc[2].x = fmaf(x.z, w.x, acc[2].x); acc[2].y = fmaf(x.z, w.y, acc[2].y); acc[2].z = fmaf(x.z, w.z, acc[2].z); acc[2].w = fmaf(x.z, w.w, acc[2].w);
+            acc[3].x = fmaf(x.w, w.x, acc[3].x); acc[3].y = fmaf(x.w, w.y, acc[3].y); acc[3].z = fmaf(x.w, w.z, acc[3].z); acc[3].w = fmaf(x.w, w.w, acc[3].w);
+        }
+#pragma unroll
+        for (int i = 0; i < SE_IMG; i++) reinterpret_cast<float4*>(part + ((size_t)sl * SE_IMG + i) * N)[g] = acc[i];
+    }
+    return slices;
+}
+
 __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
                                                     const float* __restrict__ b1, const float* __restrict__ w2,
                                                     const float* __restrict__ b2, float* __restrict__ scale,
-                                                    int C, int SQ, float inv_hw) {
-    __shared__ float m[576];
-    __shared__ float hid[144];
-    const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) m[i] = pool[(int64_t)b * C + i] * inv_hw;
-    __syncthreads();
-    for (int j = threadIdx.x; j < SQ; j += blockDim.x) {
-        float a0 = b1[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;                 // C % 8 == 0; 8 independent loads in flight
-#pragma unroll 2
-        for (int c = 0; c < C; c += 4) {
-            a0 = fmaf(m[c], __ldg(w1 + (int64_t)c * SQ + j), a0); a1 = fmaf(m[c + 1], __ldg(w1 + (int64_t)(c + 1) * SQ + j), a1);
-            a2 = fmaf(m[c + 2], __ldg(w1 + (int64_t)(c + 2) * SQ + j), a2); a3 = fmaf(m[c + 3], __ldg(w1 + (int64_t)(c + 3) * SQ + j), a3);
-        }
-        hid[j] = fmaxf((a0 + a1) + (a2 + a3), 0.f);
+                                                    int B, int C, int SQ, float inv_hw) {
+    static_assert(SE_IMG == 4, "se_fc_partial reads the 4 images' inputs as one float4");
+    __shared__ __align__(16) float m[SE_MAXC * SE_IMG];       // [c][image]
+    __shared__ __align__(16) float hid[SE_MAXSQ * SE_IMG];    // [j][image]
+    __shared__ __align__(16) float part[SE_PART];             // [slice][image][n]
+    const int b0 = blockIdx.x * SE_IMG, tid = threadIdx.x;
+    for (int i = tid; i < C * SE_IMG; i += blockDim.x) {
+        const int img = i / C, c = i - img * C;
+        m[c * SE_IMG + img] = (b0 + img < B) ? pool[(size_t)(b0 + img) * C + c] * inv_hw : 0.f;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a0 = b2[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;                 // SQ % 8 == 0
-#pragma unroll 2
-        for (int j = 0; j < SQ; j += 4) {
-            a0 = fmaf(hid[j], __ldg(w2 + (int64_t)j * C + c), a0); a1 = fmaf(hid[j + 1], __ldg(w2 + (int64_t)(j + 1) * C + c), a1);
-            a2 = fmaf(hid[j + 2], __ldg(w2 + (int64_t)(j + 2) * C + c), a2); a3 = fmaf(hid[j + 3], __ldg(w2 + (int64_t)(j + 3) * C + c), a3);
-        }
-        scale[(int64_t)b * C + c] = apply_act((a0 + a1) + (a2 + a3), ACT_HSIGMOID);
+    const int s1 = se_fc_partial(w1, m, C, SQ, part);
+    __syncthreads();
+    for (int i = tid; i < SQ * SE_IMG; i += blockDim.x) {
+        const int img = i / SQ, j = i - img * SQ;
+        float a = b1[j];
+        for (int sl = 0; sl < s1; sl++) a += part[((size_t)sl * SE_IMG + img) * SQ + j];
+        hid[j * SE_IMG + img] = fmaxf(a, 0.f);
     }
+    __syncthreads();
+    const int s2 = se_fc_partial(w2, hid, SQ, C, part);
+    __syncthreads();
+    for (int i = tid; i < C * SE_IMG; i += blockDim.x) {
+        const int img = i / C, c = i - img * C;
+        if (b0 + img >= B) break;
+        float a = b2[c];
+        for (int sl = 0; sl < s2; sl++) a += part[((size_t)sl * SE_IMG + img) * C + c];
+        scale[(size_t)(b0 + img) * C + c] = apply_act(a, ACT_HSIGMOID);
+    }
+}
+
+static int launch_se_fc(const MBBlock& m, const float* pool, float* scale, int B, float inv_hw, cudaStream_t s) {
+    if (m.exp > SE_MAXC || m.sq > SE_MAXSQ || (m.exp & 3) || (m.sq & 3)) { set_error("se_fc: unsupported SE shape %d -> %d", m.exp, m.sq); return KPD_ERR_UNSUPPORTED; }
+    se_fc_kernel<<<(B + SE_IMG - 1) / SE_IMG, 256, 0, s>>>(pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
+    KPD_LAUNCH_CHECK();
+    return 0;
 }
 
 static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, cudaStream_t s) {
@@ -288,8 +334,7 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
         if (m.se) { KPD_CUDA(cudaMemsetAsync(se_pool, 0, sizeof(float) * B * m.exp, s)); pool = se_pool; }
         KPD_TRY(depthwise_batched(m, x, dwout, pool, B, H, p->sm_count, s));
         if (m.se) {
-            se_fc_kernel<<<B, 256, 0, s>>>(se_pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, se_scale, m.exp, m.sq, 1.f / (float)(Ho * Ho));
-            KPD_LAUNCH_CHECK();
+            KPD_TRY(launch_se_fc(m, se_pool, se_scale, B, 1.f / (float)(Ho * Ho), s));
         }
         float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
         PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
@@ -343,8 +388,7 @@ int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp
         KPD_TRY(launch_dw(m, x, dwout, pool, B, H, s));
         const float* scale = nullptr;
         if (m.se) {
-            se_fc_kernel<<<B, 256, 0, s>>>(se_pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, se_scale, m.exp, m.sq, 1.f / (float)(Ho * Ho));
-            KPD_LAUNCH_CHECK();
+            KPD_TRY(launch_se_fc(m, se_pool, se_scale, B, 1.f / (float)(Ho * Ho), s));
             scale = se_scale;
         }
         // block outputs that the FPN consumes are written straight into their feat slot (features.3 / features.8)
@@ -367,19 +411,32 @@ __global__ void __launch_bounds__(256) lateral0_kernel(const float* __restrict__
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) ws4[i >> 5][i & 31] = __ldg(reinterpret_cast<const float4*>(w) + i);
     __syncthreads();
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int Wc = W / up, Hc = H / up;
+    // 32-bit index arithmetic throughout (the host checks pixels < 2^31): 64-bit div/mod costs more than the 64 FMAs per pixel
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t Wc = W / up, Hc = H / up, npix = (uint32_t)pixels;
     constexpr int PX = 4;                                  // pixels in flight per warp iteration
-    for (int64_t p0 = warp * PX; p0 < pixels; p0 += nwarps * PX) {
+    const bool quad = (W % PX == 0) && (up % PX == 0);     // the 4 pixels share one coarse (top-down) pixel
+    for (uint32_t p0 = warp * PX; p0 < npix; p0 += nwarps * PX) {
         float4 xv[PX][4], acc[PX];
 #pragma unroll
         for (int j = 0; j < PX; j++) {
-            const int64_t p = min(p0 + j, pixels - 1);
-            const float4* ip = reinterpret_cast<const float4*>(feat0 + p * 16);
+            const uint32_t p = min(p0 + j, npix - 1);
+            const float4* ip = reinterpret_cast<const float4*>(feat0 + (size_t)p * 16);
             xv[j][0] = __ldg(ip); xv[j][1] = __ldg(ip + 1); xv[j][2] = __ldg(ip + 2); xv[j][3] = __ldg(ip + 3);
-            const int x = (int)(p % W), y = (int)((p / W) % H); const int64_t b = p / ((int64_t)W * H);
-            acc[j] = __ldg(reinterpret_cast<const float4*>(coarse + ((b * Hc + y / up) * Wc + x / up) * 128) + lane);
+        }
+        if (quad) {
+            const uint32_t row = p0 / (uint32_t)W, x = p0 - row * W, b = row / (uint32_t)H, y = row - b * H;
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(coarse + ((size_t)(b * Hc + y / up) * Wc + x / up) * 128) + lane);
+#pragma unroll
+            for (int j = 0; j < PX; j++) acc[j] = cv;
+        } else {
+#pragma unroll
+            for (int j = 0; j < PX; j++) {
+                const uint32_t p = min(p0 + j, npix - 1);
+                const uint32_t row = p / (uint32_t)W, x = p - row * W, b = row / (uint32_t)H, y = row - b * H;
+                acc[j] = __ldg(reinterpret_cast<const float4*>(coarse + ((size_t)(b * Hc + y / up) * Wc + x / up) * 128) + lane);
+            }
         }
 #pragma unroll
         for (int k4 = 0; k4 < 4; k4++) {
@@ -395,10 +452,10 @@ __global__ void __launch_bounds__(256) lateral0_kernel(const float* __restrict__
         }
 #pragma unroll
         for (int j = 0; j < PX; j++) {
-            if (p0 + j >= pixels) break;
+            if (p0 + j >= npix) break;
             float4 a = acc[j];
             if (round_tf32) { a.x = tf32_rna(a.x); a.y = tf32_rna(a.y); a.z = tf32_rna(a.z); a.w = tf32_rna(a.w); }
-            reinterpret_cast<float4*>(out + (p0 + j) * 128)[lane] = a;
+            reinterpret_cast<float4*>(out + (size_t)(p0 + j) * 128)[lane] = a;
         }
     }
 }
@@ -413,6 +470,7 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
                      reinterpret_cast<float*>(scratch + sm.lat2), reinterpret_cast<float*>(scratch + sm.lat3)};
     const int hs[4] = {S / 2, S / 8, S / 16, S / 32};
     const int cin[4] = {16, 24, 48, 576};
+    if ((int64_t)B * hs[0] * hs[0] >= (int64_t)1 << 31) { set_error("fpn laterals: B*H*W = %lld pixels exceeds the 32-bit pixel index", (long long)B * hs[0] * hs[0]); return KPD_ERR_UNSUPPORTED; }
     for (int i = 3; i >= 1 && !strict_fp32; i--) {     // tensor-core laterals 3..1 (3xTF32 GEMM + nearest-upsample add)
         PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.out = lat[i];
         a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];

@@ -8,6 +8,7 @@
 // host in mma.sync m16n8k8 order (hi/lo TF32 split) and come from L1/L2.  3xTF32 (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,
 // fp32 accumulate) keeps the trunk at fp32-level accuracy, which the channel top-k needs.
 #include "kpd_common.cuh"
+#include <stdlib.h>
 
 namespace kpd {
 
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
     extern __shared__ __align__(16) float As_all[];      // [PW_STAGES][PW_BM * PW_LDA]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
     const int n8 = p.N >> 3, K = p.K;
+    const uint32_t M = (uint32_t)p.M;                    // 32-bit pixel indices (host-checked): no 64-bit div/mod on the item path
     const int sk4 = tid & 7, srow = tid >> 3;            // staging map: float4 (row = srow + 32*i, k4 = sk4), i = 0..3
     const int total = tiles_m * tiles_n;
 
@@ -51,13 +53,13 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
     auto issue_load = [&](int stage) {
         if (l_item < total) {
             float* dst = As_all + (size_t)stage * (PW_BM * PW_LDA);
-            const int64_t m0 = (int64_t)(l_item / tiles_n) * PW_BM;
+            const uint32_t m0 = (uint32_t)(l_item / tiles_n) * PW_BM;
             const int k = l_kc + sk4 * 4;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int64_t m = m0 + srow + 32 * i;
-                const bool ok = (m < p.M) && (k < K);
-                cp_async16(dst + (srow + 32 * i) * PW_LDA + sk4 * 4, ok ? (const void*)(p.A + m * K + k) : (const void*)p.A, ok);
+                const uint32_t m = m0 + srow + 32 * i;
+                const bool ok = (m < M) && (k < K);
+                cp_async16(dst + (srow + 32 * i) * PW_LDA + sk4 * 4, ok ? (const void*)(p.A + (size_t)m * K + k) : (const void*)p.A, ok);
             }
             l_kc += PW_KC;
             if (l_kc >= K) { l_kc = 0; l_item += gridDim.x; }
@@ -69,13 +71,14 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
 
     int stage = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        const int64_t m0 = (int64_t)(item / tiles_n) * PW_BM;
-        const int nt0 = (item % tiles_n) * PW_NT, ntc = min(PW_NT, n8 - nt0);
-        const int64_t r[2] = {m0 + warp * 16 + g, m0 + warp * 16 + g + 8};
+        const int tm = item / tiles_n;
+        const uint32_t m0 = (uint32_t)tm * PW_BM;
+        const int nt0 = (item - tm * tiles_n) * PW_NT, ntc = min(PW_NT, n8 - nt0);
+        const uint32_t r[2] = {m0 + warp * 16 + g, m0 + warp * 16 + g + 8};
         const float* sc0 = nullptr; const float* sc1 = nullptr;
         if (p.se_scale) {
-            sc0 = p.se_scale + (min(r[0], p.M - 1) / p.hw) * K + t;
-            sc1 = p.se_scale + (min(r[1], p.M - 1) / p.hw) * K + t;
+            sc0 = p.se_scale + (size_t)(min(r[0], M - 1) / (uint32_t)p.hw) * K + t;
+            sc1 = p.se_scale + (size_t)(min(r[1], M - 1) / (uint32_t)p.hw) * K + t;
         }
         float acc[PW_NT][4];
 #pragma unroll
@@ -114,14 +117,14 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
             stage = (stage + 1) % PW_STAGES;
         }
         // epilogue: rows r0 = g, r1 = g + 8 of this warp's 16-row slab; columns n = (nt0+j)*8 + 2t, +1
-        int64_t rbase[2] = {0, 0};
+        size_t rbase[2] = {0, 0};
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            if (r[h] >= p.M) continue;
-            if (p.res_mode == 1) rbase[h] = r[h] * p.N;
+            if (r[h] >= M) continue;
+            if (p.res_mode == 1) rbase[h] = (size_t)r[h] * p.N;
             else if (p.res_mode == 2) {
-                const int x = (int)(r[h] % p.W), y = (int)((r[h] / p.W) % p.H); const int64_t b = r[h] / ((int64_t)p.W * p.H);
-                rbase[h] = ((b * (p.H / p.up) + y / p.up) * (p.W / p.up) + x / p.up) * p.N;
+                const uint32_t row = r[h] / (uint32_t)p.W, x = r[h] - row * p.W, b = row / (uint32_t)p.H, y = row - b * p.H;
+                rbase[h] = ((size_t)(b * (p.H / p.up) + y / p.up) * (p.W / p.up) + x / p.up) * p.N;
             }
         }
 #pragma unroll
@@ -131,14 +134,14 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
             const float b0 = p.bias ? __ldg(p.bias + n) : 0.f, b1 = p.bias ? __ldg(p.bias + n + 1) : 0.f;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                if (r[h] >= p.M) continue;
+                if (r[h] >= M) continue;
                 float v0 = apply_act(acc[j][2 * h] + b0, p.act), v1 = apply_act(acc[j][2 * h + 1] + b1, p.act);
                 if (p.res_mode) {
                     const float2 q = __ldg(reinterpret_cast<const float2*>(p.res + rbase[h] + n));
                     v0 += q.x; v1 += q.y;
                 }
                 if (p.round_tf32) { v0 = tf32_rna(v0); v1 = tf32_rna(v1); }
-                *reinterpret_cast<float2*>(p.out + r[h] * p.N + n) = make_float2(v0, v1);
+                *reinterpret_cast<float2*>(p.out + (size_t)r[h] * p.N + n) = make_float2(v0, v1);
             }
         }
     }
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
 int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s) {
     if ((p.K & 7) || (p.N & 7)) { set_error("pointwise_mma: K and N must be multiples of 8 (got %d, %d)", p.K, p.N); return KPD_ERR_UNSUPPORTED; }
     if (p.M <= 0) return 0;
+    if (p.M >= ((int64_t)1 << 31) - PW_BM) { set_error("pointwise_mma: M = %lld pixels exceeds the 32-bit pixel index", (long long)p.M); return KPD_ERR_UNSUPPORTED; }
     const int tiles_m = (int)((p.M + PW_BM - 1) / PW_BM), tiles_n = ((p.N >> 3) + PW_NT - 1) / PW_NT;
     const size_t smem = sizeof(float) * PW_STAGES * PW_BM * PW_LDA;           // 72 KB: 2-3 CTAs per SM
     static uint64_t attr_mask = 0;
@@ -264,7 +268,11 @@ __global__ void __launch_bounds__(256, 2) dw_tiled_kernel(const float* __restric
     }
 }
 
+int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s);
+
 int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s) {
+    static const bool tiled = getenv("KPD_DW_TILED") != nullptr;      // predecessor kept for A/B timing (tools/bench_micro)
+    if (!tiled) return depthwise_tma(m, in, out, pool, B, H, sm_count, s);
     const int Ho = H / m.stride, C = m.exp;
     if (C & 3) { set_error("depthwise_batched: unsupported channel count %d", C); return KPD_ERR_UNSUPPORTED; }
     // channel group: <= 32 channels with (group/4) dividing 256 for every group incl. the last partial one
