@@ -140,6 +140,7 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     KPD_TRY(check_layout(plan, d_workspace, layout));
     KPD_CHECK_ARG(d_images != nullptr, "kpd_backbone_fpn0: null images");
     KPD_CHECK_ARG(B > 0 && B <= 65535 && S > 0 && S % 32 == 0, "kpd_backbone_fpn0: bad batch/size %d/%d", B, S);
+    KPD_CHECK_ARG((int64_t)B * (S / 2) * (S / 2) < ((int64_t)1 << 30), "kpd_backbone_fpn0: B*(S/2)^2 = %lld exceeds the 32-bit pixel index of the trunk kernels", (long long)B * (S / 2) * (S / 2));
     KPD_CHECK_ARG(precision >= 0 && precision <= 2, "unknown precision %d", precision);
     const kpd_workspace_layout& L = *layout;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -11,15 +11,6 @@ namespace kpd {
 
 int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out, int B, int H, int strict_fp32, cudaStream_t s);
 
-struct PwMma {
-    const float* A; const float4* Wf; const float* bias; float* out;
-    int64_t M; int K, N, act;
-    const float* se_scale; int hw;
-    const float* res; int res_mode;
-    int H, W, up;
-    int round_tf32;
-};
-int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s);
 int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
@@ -33,12 +24,12 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
     for (int i = threadIdx.x; i < 9 * Cin * 16; i += blockDim.x) ws[i] = w[i];
     if (threadIdx.x < 16) bs[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
-    const int Ho = S / 2;
-    const int64_t total = (int64_t)B * Ho * Ho * 4;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t Ho = S / 2;
+    const uint32_t total = (uint32_t)B * Ho * Ho * 4;       // 32-bit index arithmetic (host-checked): 64-bit div/mod would dominate the 36 FMAs
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const int q = (int)(t & 3);
-        const int64_t pix = t >> 2;
-        const int ox = (int)(pix % Ho), oy = (int)((pix / Ho) % Ho), b = (int)(pix / ((int64_t)Ho * Ho));
+        const uint32_t pix = t >> 2, rowi = pix / Ho;
+        const int ox = (int)(pix - rowi * Ho), b = (int)(rowi / Ho), oy = (int)(rowi - (uint32_t)b * Ho);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         for (int c = 0; c < Cin; c++) {
             const float* ip = in + ((int64_t)b * Cin + c) * S * S;
@@ -326,7 +317,7 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
         const int Ho = H / m.stride;
         const float* x = cur;
         if (m.w_exp) {
-            PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act;
+            PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act;
             KPD_TRY(pointwise_mma(a, p->sm_count, s));
             x = expand;
         }
@@ -337,12 +328,12 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
             KPD_TRY(launch_se_fc(m, se_pool, se_scale, B, 1.f / (float)(Ho * Ho), s));
         }
         float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
-        PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
+        PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.Wraw = m.w_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
         a.se_scale = m.se ? se_scale : nullptr; a.hw = Ho * Ho; a.res = m.res ? cur : nullptr; a.res_mode = m.res ? 1 : 0;
         KPD_TRY(pointwise_mma(a, p->sm_count, s));
         cur = dst; H = Ho;
     }
-    PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH;
+    PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.Wraw = p->w_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH;
     return pointwise_mma(a, p->sm_count, s);
 }
 
@@ -460,6 +451,71 @@ __global__ void __launch_bounds__(256) lateral0_kernel(const float* __restrict__
     }
 }
 
+// lateral 0, quad form (W % 4 == 0 and up % 4 == 0: the 4 pixels of an aligned quad share one top-down pixel).  A lane keeps
+// its 4 output channels' 16 x 4 weights in registers for the whole kernel; a warp iteration streams one quad: the quad's
+// 4 x 16 inputs are fetched as ONE coalesced 256-byte row (8 B per lane) and re-read as shared-memory broadcasts, the next
+// quad's input and top-down vectors are prefetched into registers before the 256 FMAs of the current one, and the result
+// leaves as four 512-byte rows.  The 1.64 GB fp32 output (B = 256) makes this the trunk's largest HBM stream.
+__global__ void __launch_bounds__(256, 2) lateral0_quad_kernel(const float* __restrict__ feat0, const float* __restrict__ w,
+                                                               const float* __restrict__ coarse, float* __restrict__ out,
+                                                               uint32_t nquads, int H, int W, int up, int round_tf32) {
+    __shared__ __align__(16) float xs[8][2][64];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float4 wr[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) wr[k] = __ldg(reinterpret_cast<const float4*>(w) + k * 32 + lane);
+    const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t Wc = W / up, Hc = H / up;
+    auto fetch = [&](uint32_t q, float2& x, float4& c) {
+        x = __ldg(reinterpret_cast<const float2*>(feat0 + (size_t)q * 64) + lane);
+        const uint32_t p0 = q * 4, row = p0 / (uint32_t)W, xq = p0 - row * W, b = row / (uint32_t)H, y = row - b * H;
+        c = __ldg(reinterpret_cast<const float4*>(coarse + ((size_t)(b * Hc + y / up) * Wc + xq / up) * 128) + lane);
+    };
+    uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float2 xn = make_float2(0.f, 0.f); float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nquads) fetch(q, xn, cn);
+    int buf = 0;
+    for (; q < nquads; q += nw) {
+        const float4 cc = cn;
+        *reinterpret_cast<float2*>(&xs[wid][buf][lane * 2]) = xn;
+        __syncwarp();                                       // also orders this write after every lane's reads two iterations back
+        if (q + nw < nquads) fetch(q + nw, xn, cn);
+        float4 acc[4] = {cc, cc, cc, cc};
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 xx = *reinterpret_cast<const float4*>(&xs[wid][buf][j * 16 + k4 * 4]);      // broadcast
+                const float4 w0 = wr[k4 * 4 + 0], w1 = wr[k4 * 4 + 1], w2 = wr[k4 * 4 + 2], w3 = wr[k4 * 4 + 3];
+                acc[j].x = fmaf(xx.x, w0.x, acc[j].x); acc[j].y = fmaf(xx.x, w0.y, acc[j].y); acc[j].z = fmaf(xx.x, w0.z, acc[j].z); acc[j].w = fmaf(xx.x, w0.w, acc[j].w);
+                acc[j].x = fmaf(xx.y, w1.x, acc[j].x); acc[j].y = fmaf(xx.y, w1.y, acc[j].y); acc[j].z = fmaf(xx.y, w1.z, acc[j].z); acc[j].w = fmaf(xx.y, w1.w, acc[j].w);
+                acc[j].x = fmaf(xx.z, w2.x, acc[j].x); acc[j].y = fmaf(xx.z, w2.y, acc[j].y); acc[j].z = fmaf(xx.z, w2.z, acc[j].z); acc[j].w = fmaf(xx.z, w2.w, acc[j].w);
+                acc[j].x = fmaf(xx.w, w3.x, acc[j].x); acc[j].y = fmaf(xx.w, w3.y, acc[j].y); acc[j].z = fmaf(xx.w, w3.z, acc[j].z); acc[j].w = fmaf(xx.w, w3.w, acc[j].w);
+            }
+        }
+        float4* op = reinterpret_cast<float4*>(out + (size_t)q * 512) + lane;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float4 a = acc[j];
+            if (round_tf32) { a.x = tf32_rna(a.x); a.y = tf32_rna(a.y); a.z = tf32_rna(a.z); a.w = tf32_rna(a.w); }
+            op[j * 32] = a;
+        }
+        buf ^= 1;
+    }
+}
+
+static int launch_lateral0(const float* feat0, const float* w, const float* coarse, float* out, int64_t pixels, int H, int W, int up,
+                           int round_tf32, int sm_count, cudaStream_t s) {
+    if ((W % 4 == 0) && (up % 4 == 0)) {
+        lateral0_quad_kernel<<<sm_count * 2, 256, 0, s>>>(feat0, w, coarse, out, (uint32_t)(pixels / 4), H, W, up, round_tf32);
+    } else {
+        const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)sm_count * 8);
+        lateral0_kernel<<<grid, 256, 0, s>>>(feat0, w, coarse, out, pixels, H, W, up, round_tf32);
+    }
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
 // FPN laterals + top-down pathway (backbone.py:33-37): lat3 = L3(f3); lat2 = L2(f2)+up2(lat3); lat1 = L1(f1)+up2(lat2);
 // lateral0 = L0(f0) + up4(lat1)  -> written to the workspace as the input of fpn_convs[0].
 int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
@@ -472,7 +528,7 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
     const int cin[4] = {16, 24, 48, 576};
     if ((int64_t)B * hs[0] * hs[0] >= (int64_t)1 << 31) { set_error("fpn laterals: B*H*W = %lld pixels exceeds the 32-bit pixel index", (long long)B * hs[0] * hs[0]); return KPD_ERR_UNSUPPORTED; }
     for (int i = 3; i >= 1 && !strict_fp32; i--) {     // tensor-core laterals 3..1 (3xTF32 GEMM + nearest-upsample add)
-        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.out = lat[i];
+        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.Wraw = p->w_lat[i]; a.out = lat[i];
         a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
         KPD_TRY(pointwise_mma(a, p->sm_count, s));
@@ -487,21 +543,15 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
             KPD_TRY(conv_dense_umma(p, p->lat0_conv, 0, ws + L.feat[0], lat[0], 0, B, hs[0], hs[0], ACT_NONE, round_tf32, nullptr, s,
                                     nullptr, lat[1], hs[0] / hs[1]));
         } else {
-            const int64_t pixels = (int64_t)B * hs[0] * hs[0];
-            const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)p->sm_count * 8);
-            lateral0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0],
-                                                 pixels, hs[0], hs[0], hs[0] / hs[1], round_tf32);
-            KPD_LAUNCH_CHECK();
+            KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
+                                    hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
         }
     }
     if (!strict_fp32) return 0;
     for (int i = 3; i >= 0; i--) {
         if (i == 0) {
-            const int64_t pixels = (int64_t)B * hs[0] * hs[0];
-            const int grid = (int)std::min<int64_t>((pixels + 31) / 32, (int64_t)p->sm_count * 8);
-            lateral0_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0],
-                                                 pixels, hs[0], hs[0], hs[0] / hs[1], round_tf32);
-            KPD_LAUNCH_CHECK();
+            KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
+                                    hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
             break;
         }
         PwArgs a{}; a.in = reinterpret_cast<const float*>(ws + L.feat[i]); a.w = p->w_lat[i]; a.bias = nullptr; a.out = lat[i];

@@ -135,4 +135,17 @@ int conv_dense_umma(const kpd_plan* p, const DenseConv& c, int prec_bf16, const 
                     float* pool_part = nullptr, const float* res = nullptr, int res_up = 1);
 int pointwise(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
               int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s);
+// Batch-wide pointwise (1x1) convolution as a GEMM over all pixels: out[M][N] = act(A[M][K] * W[K][N] + bias) (+ residual).
+struct PwMma {
+    const float* A; const float4* Wf; const float* bias; float* out;   // Wf: 3xTF32 mma.sync B fragments (kpd_pw.cu)
+    int64_t M; int K, N, act;
+    const float* se_scale; int hw;           // optional [image][K] scale applied to A (SE excitation), hw = pixels/image
+    const float* res; int res_mode;          // 0 none, 1 same-shape add, 2 nearest-upsampled add (FPN top-down)
+    int H, W, up;                            // res_mode 2: output map H x W, coarse map (H/up) x (W/up), N channels
+    int round_tf32;                          // round the result to tf32 (it feeds a kind::tf32 tcgen05 MMA)
+    const float* Wraw;                       // [K][N] row-major fp32 (CUDA-core FFMA GEMM, kpd_pwf.cu)
+};
+int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s);
+int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s);
+
 }  // namespace kpd

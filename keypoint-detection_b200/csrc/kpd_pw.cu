@@ -18,14 +18,6 @@ __device__ __forceinline__ void mma_tf32_pw(float (&d)[4], const uint32_t (&a)[4
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-struct PwMma {
-    const float* A; const float4* Wf; const float* bias; float* out;
-    int64_t M; int K, N, act;
-    const float* se_scale; int hw;           // optional [image][K] scale applied to A (SE excitation), hw = pixels/image
-    const float* res; int res_mode;          // 0 none, 1 same-shape add, 2 nearest-upsampled add (FPN top-down)
-    int H, W, up;                            // res_mode 2: output map H x W, coarse map (H/up) x (W/up), N channels
-    int round_tf32;                          // round the result to tf32 (it feeds a kind::tf32 tcgen05 MMA)
-};
 
 constexpr int PW_BM = 128, PW_KC = 32, PW_LDA = PW_KC + 4, PW_NT = 16, PW_THREADS = 256;
 
@@ -149,6 +141,8 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
 }
 
 int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s) {
+    static const bool use_mma = getenv("KPD_PW_MMA") != nullptr;     // 3xTF32 mma.sync predecessor, kept for A/B timing
+    if (!use_mma && p.Wraw) return pointwise_ffma(p, sm_count, s);
     if ((p.K & 7) || (p.N & 7)) { set_error("pointwise_mma: K and N must be multiples of 8 (got %d, %d)", p.K, p.N); return KPD_ERR_UNSUPPORTED; }
     if (p.M <= 0) return 0;
     if (p.M >= ((int64_t)1 << 31) - PW_BM) { set_error("pointwise_mma: M = %lld pixels exceeds the 32-bit pixel index", (long long)p.M); return KPD_ERR_UNSUPPORTED; }

@@ -1,0 +1,221 @@
+// Batch-wide pointwise (1x1) convolution as an fp32 CUDA-core GEMM: out[M][N] = act(A[M][K] * W[K][N] + bias) (+ residual).
+//   reference ops: every 1x1 conv of the trunk -- tv:models/mobilenetv3.py:87-108 (expand / project), features.12 -- and
+//   dll/models/backbone.py:33-37 (FPN laterals 1..3 + nearest top-down add).
+//
+// Why CUDA cores: on sm_100a the legacy mma.sync path issues about one m16n8k8 TF32 MMA per 14 clk per SM (measured),
+// i.e. ~73 MAC/clk/SM, and the 3xTF32 split this trunk needs for fp32-level accuracy divides that by three; 128 FFMA
+// lanes deliver 128 MAC/clk/SM in exact fp32.  (tcgen05 would need the hi/lo operand split materialised in shared memory;
+// these GEMMs have K <= 576 and are bound by their activation streams once the math runs at FFMA rate.)
+//
+// Structure: persistent CTAs walk (128-row tile, column chunk) items; A rows (K-contiguous NHWC pixels) and the matching
+// W[k-chunk][column chunk] stream through a 3-stage cp.async ring that runs ahead across item boundaries.  A lane owns R
+// rows (lane, lane+32, ...), a warp owns an NT-wide column strip: the A operand is one conflict-free LDS.128 per row per 4 k
+// (row pitch 36 floats), the W operand a shared-memory broadcast, so 4*R*NT FMAs are issued per R + NT shared loads.  (R, NT)
+// is picked per layer so that narrow outputs (N = 16 ... 96) still occupy all 8 warps.  The SE excitation is applied to the
+// A tile in shared memory by the thread that copied it; bias / activation / residual (same-shape or nearest-upsampled) /
+// tf32 rounding are fused in the epilogue.
+#include "kpd_common.cuh"
+#include <stdlib.h>
+
+namespace kpd {
+
+constexpr int PF_BM = 128, PF_KC = 32, PF_LDA = PF_KC + 4, PF_STAGES = 3, PF_THREADS = 256, PF_MAXCOVER = 128;
+
+__device__ __forceinline__ void pf_cp_async16(void* smem, const void* gmem, bool valid) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;                       // src-size 0 => 16 bytes of zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(sz) : "memory");
+}
+
+struct ActNone  { __device__ __forceinline__ float operator()(float x) const { return x; } };
+struct ActRelu  { __device__ __forceinline__ float operator()(float x) const { return fmaxf(x, 0.f); } };
+struct ActHswish { __device__ __forceinline__ float operator()(float x) const { return x * fminf(fmaxf(x + 3.f, 0.f), 6.f) * (1.f / 6.f); } };
+
+// R rows per lane, NT columns per warp strip; WS = 2R strips side by side, RG = 4/R row groups of 32R rows.
+template <int R, int NT>
+__global__ void __launch_bounds__(PF_THREADS, 2) pw_ffma_kernel(const PwMma p, int tiles_m, int nchunks, int chunk_cols) {
+    constexpr int WS = 2 * R, COVER = WS * NT, STAGE_A = PF_BM * PF_LDA, STAGE_W = PF_KC * COVER;
+    constexpr int WV = COVER / 4;                          // float4 per staged W row
+    extern __shared__ __align__(16) float pf_smem[];       // [PF_STAGES][STAGE_A + STAGE_W]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int strip = warp % WS, rg = warp / WS;
+    const int K = p.K, N = p.N;
+    const uint32_t M = (uint32_t)p.M;
+    const int sk4 = tid & 7, srow = tid >> 3;              // A staging map: float4 (row = srow + 32*i, k4 = sk4), i = 0..3
+    const int total = tiles_m * nchunks;
+
+    int l_item = blockIdx.x, l_kc = 0;                     // load cursor (runs ahead of the compute cursor)
+    auto issue_load = [&](int stage) {
+        if (l_item < total) {
+            float* dstA = pf_smem + (size_t)stage * (STAGE_A + STAGE_W);
+            float* dstW = dstA + STAGE_A;
+            const int tm = l_item / nchunks, n0 = (l_item - tm * nchunks) * chunk_cols;
+            const uint32_t m0 = (uint32_t)tm * PF_BM;
+            const int k = l_kc + sk4 * 4;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t m = m0 + srow + 32 * i;
+                const bool ok = (m < M) && (k < K);
+                pf_cp_async16(dstA + (srow + 32 * i) * PF_LDA + sk4 * 4, ok ? (const void*)(p.A + (size_t)m * K + k) : (const void*)p.A, ok);
+            }
+#pragma unroll
+            for (int j = 0; j < (PF_KC * WV + PF_THREADS - 1) / PF_THREADS; j++) {
+                const int idx = tid + j * PF_THREADS;
+                if (idx < PF_KC * WV) {
+                    const int wr = idx / WV, wc = (idx - wr * WV) * 4;
+                    const bool ok = (l_kc + wr < K) && (wc < chunk_cols) && (n0 + wc < N);
+                    pf_cp_async16(dstW + wr * COVER + wc, ok ? (const void*)(p.Wraw + (size_t)(l_kc + wr) * N + n0 + wc) : (const void*)p.Wraw, ok);
+                }
+            }
+            l_kc += PF_KC;
+            if (l_kc >= K) { l_kc = 0; l_item += gridDim.x; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < PF_STAGES - 1; s++) issue_load(s);
+
+    int stage = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        const int tm = item / nchunks, n0 = (item - tm * nchunks) * chunk_cols;
+        const uint32_t m0 = (uint32_t)tm * PF_BM;
+        const int ncols = min(chunk_cols, N - n0);            // columns of this chunk
+        const bool busy = strip * NT < ncols;
+        const int rbase = rg * (32 * R) + lane;                // tile row of this lane's first row; row i -> rbase + 32*i
+        uint32_t simg[4] = {0, 0, 0, 0};                       // SE: image of the 4 rows this thread stages
+        if (p.se_scale) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) simg[i] = min(m0 + srow + 32 * i, M - 1) / (uint32_t)p.hw;
+        }
+        float acc[R][NT];
+#pragma unroll
+        for (int i = 0; i < R; i++)
+#pragma unroll
+            for (int j = 0; j < NT; j++) acc[i][j] = 0.f;
+
+        for (int kc = 0; kc < K; kc += PF_KC) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(PF_STAGES - 2) : "memory");
+            float* As = pf_smem + (size_t)stage * (STAGE_A + STAGE_W);
+            const float* Ws = As + STAGE_A;
+            if (p.se_scale) {                                  // scale the chunks this thread copied (its own cp.async data has landed)
+                const int k = kc + sk4 * 4;
+                if (k < K) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float4* ap = reinterpret_cast<float4*>(As + (srow + 32 * i) * PF_LDA + sk4 * 4);
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.se_scale + (size_t)simg[i] * K + k));
+                        float4 v = *ap; v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w; *ap = v;
+                    }
+                }
+            }
+            __syncthreads();                                   // chunk `stage` is visible; everyone is done with the slot refilled next
+            issue_load((stage + PF_STAGES - 1) % PF_STAGES);
+            if (busy) {
+                const int k4n = min(PF_KC, K - kc) >> 2;
+                const float* ap = As + rbase * PF_LDA;
+                const float* wp = Ws + strip * NT;
+#pragma unroll 1
+                for (int k4 = 0; k4 < k4n; k4++) {
+                    float4 a[R];
+#pragma unroll
+                    for (int i = 0; i < R; i++) a[i] = *reinterpret_cast<const float4*>(ap + i * 32 * PF_LDA + k4 * 4);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+                        for (int c4 = 0; c4 < NT / 4; c4++) {
+                            const float4 w = *reinterpret_cast<const float4*>(wp + (k4 * 4 + kk) * COVER + c4 * 4);   // broadcast
+#pragma unroll
+                            for (int i = 0; i < R; i++) {
+                                const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+                                acc[i][c4 * 4 + 0] = fmaf(av, w.x, acc[i][c4 * 4 + 0]); acc[i][c4 * 4 + 1] = fmaf(av, w.y, acc[i][c4 * 4 + 1]);
+                                acc[i][c4 * 4 + 2] = fmaf(av, w.z, acc[i][c4 * 4 + 2]); acc[i][c4 * 4 + 3] = fmaf(av, w.w, acc[i][c4 * 4 + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+            stage = (stage + 1) % PF_STAGES;
+        }
+        if (!busy) continue;
+        // epilogue: this lane's R rows x the strip's columns (N % 4 == 0, so float4 groups are all-in or all-out)
+        const int nb = n0 + strip * NT;
+        auto epilogue = [&](auto actfn) {
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                const uint32_t r = m0 + rbase + 32 * i;
+                if (r >= M) continue;
+                const float* resp = nullptr;
+                if (p.res_mode == 1) resp = p.res + (size_t)r * N;
+                else if (p.res_mode == 2) {
+                    const uint32_t row = r / (uint32_t)p.W, x = r - row * p.W, b = row / (uint32_t)p.H, y = row - b * p.H;
+                    resp = p.res + ((size_t)(b * (p.H / p.up) + y / p.up) * (p.W / p.up) + x / p.up) * N;
+                }
+                float* op = p.out + (size_t)r * N;
+#pragma unroll
+                for (int c4 = 0; c4 < NT / 4; c4++) {
+                    const int n = nb + c4 * 4;
+                    if (strip * NT + c4 * 4 >= ncols) break;
+                    float4 v = make_float4(acc[i][c4 * 4], acc[i][c4 * 4 + 1], acc[i][c4 * 4 + 2], acc[i][c4 * 4 + 3]);
+                    if (p.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n)); v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w; }
+                    v.x = actfn(v.x); v.y = actfn(v.y); v.z = actfn(v.z); v.w = actfn(v.w);
+                    if (resp) { const float4 q = __ldg(reinterpret_cast<const float4*>(resp + n)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+                    if (p.round_tf32) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+                    *reinterpret_cast<float4*>(op + n) = v;
+                }
+            }
+        };
+        if (p.act == ACT_RELU) epilogue(ActRelu());
+        else if (p.act == ACT_HSWISH) epilogue(ActHswish());
+        else epilogue(ActNone());
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// (R, NT, chunks) per layer: minimise chunks * cover * cycles-per-column of the inner loop (max of the shared-memory
+// wavefronts 8*(4R+NT) and the per-sub-partition issue slots 2*(4*R*NT+R+NT) per 4 k, over the cover of 2R*NT columns).
+struct PfCfg { int R, NT, nchunks, chunk_cols; };
+static PfCfg choose_pf_cfg(int N) {
+    PfCfg best{4, 16, 1, 128};
+    double best_cost = 1e30;
+    const int rs[3] = {4, 2, 1}, nts[2] = {16, 8};
+    for (int R : rs)
+        for (int NT : nts) {
+            const int cover = 2 * R * NT;
+            const int nchunks = (N + cover - 1) / cover;
+            int cc = ((N + nchunks - 1) / nchunks + 3) & ~3;          // even split, float4 granular
+            if (cc > cover) cc = cover;
+            const double lds = 8.0 * (4 * R + NT), iss = 2.0 * (4 * R * NT + R + NT);
+            const double cost = nchunks * std::max(lds, iss) + 0.02 * nchunks;     // (the cover cancels: cost per pass)
+            if (cost < best_cost - 1e-9) { best_cost = cost; best = PfCfg{R, NT, nchunks, cc}; }
+        }
+    return best;
+}
+
+int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s) {
+    if ((p.K & 7) || (p.N & 3)) { set_error("pointwise_ffma: K must be a multiple of 8 and N of 4 (got %d, %d)", p.K, p.N); return KPD_ERR_UNSUPPORTED; }
+    if (!p.Wraw) { set_error("pointwise_ffma: missing weights"); return KPD_ERR_ARG; }
+    if (p.M <= 0) return 0;
+    if (p.M >= ((int64_t)1 << 31) - PF_BM) { set_error("pointwise_ffma: M = %lld pixels exceeds the 32-bit pixel index", (long long)p.M); return KPD_ERR_UNSUPPORTED; }
+    const PfCfg c = choose_pf_cfg(p.N);
+    const int tiles_m = (int)((p.M + PF_BM - 1) / PF_BM);
+    const int cover = 2 * c.R * c.NT;
+    const size_t smem = sizeof(float) * PF_STAGES * (PF_BM * PF_LDA + PF_KC * cover);
+    const int grid = (int)std::min<int64_t>((int64_t)tiles_m * c.nchunks, (int64_t)sm_count * 2);
+    static uint64_t attr[6] = {};
+#define KPD_PF_LAUNCH(RR, NN, SLOT)                                                              \
+    do {                                                                                         \
+        KPD_CUDA(ensure_smem_attr(pw_ffma_kernel<RR, NN>, (int)smem, attr[SLOT]));               \
+        pw_ffma_kernel<RR, NN><<<grid, PF_THREADS, smem, s>>>(p, tiles_m, c.nchunks, c.chunk_cols); \
+    } while (0)
+    if (c.R == 4 && c.NT == 16) KPD_PF_LAUNCH(4, 16, 0);
+    else if (c.R == 4) KPD_PF_LAUNCH(4, 8, 1);
+    else if (c.R == 2 && c.NT == 16) KPD_PF_LAUNCH(2, 16, 2);
+    else if (c.R == 2) KPD_PF_LAUNCH(2, 8, 3);
+    else if (c.NT == 16) KPD_PF_LAUNCH(1, 16, 4);
+    else KPD_PF_LAUNCH(1, 8, 5);
+#undef KPD_PF_LAUNCH
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace kpd
