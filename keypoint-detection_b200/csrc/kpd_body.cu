@@ -202,78 +202,86 @@ __global__ void __launch_bounds__(256) dw_kernel(const float* __restrict__ in, c
 }
 
 // SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 ).
-// One CTA per SE_IMG images (the weight matrices are read once per CTA, not once per image: at C = 576 they are 2 x 332 KB,
-// and one-image CTAs made the layer L2-bandwidth bound).  Each layer is spread over (4-output group, k-slice) threads with
-// float4 weight loads, 8 in flight per thread, so enough bytes are outstanding to cover the L2 latency; the k-slices are
-// combined in a fixed order through shared memory (deterministic).
-constexpr int SE_IMG = 4, SE_MAXC = 576, SE_MAXSQ = 144, SE_SLICES = 8;
-constexpr int SE_PART = 4608;                             // floats: max over the layers of slices * SE_IMG * N (7*4*144 = 4032 at 576 -> 144)
+// One CTA per SE_IMG images (the weight matrices are read once per CTA, not once per image: at C = 576 they are 2 x 332 KB).
+// A layer is spread over (4-output group, k-slice) threads with the S slices of a group in ADJACENT lanes: every thread
+// streams K/S float4 weight rows (8 in flight), and the slices are combined with a shuffle butterfly -- the layer is a
+// latency chain of K/(8*S) dependent load batches instead of K/8, with no shared-memory partials.
+constexpr int SE_IMG = 4, SE_MAXC = 576, SE_MAXSQ = 144, SE_THREADS = 1024;
 
-__device__ __forceinline__ int se_fc_partial(const float* __restrict__ W, const float* v, int K, int N, float* part) {
+// out4[img] (valid in the lanes with slice 0) = sum_k v[k][img] * W[k][4g..4g+3]
+__device__ __forceinline__ bool se_fc_layer(const float* __restrict__ W, const float* v, int K, int N, float4 (&acc)[SE_IMG], int& g_out) {
     const int G = N >> 2;
-    int slices = min(min(SE_SLICES, (int)blockDim.x / G), K);
-    while (slices * SE_IMG * N > SE_PART) slices--;
-    const int tid = threadIdx.x;
-    if (tid < G * slices) {
-        const int g = tid % G, sl = tid / G;
-        const int per = (K + slices - 1) / slices, k0 = sl * per, k1 = min(K, k0 + per);
-        float4 acc[SE_IMG];
+    int S = 1;
+    while (S < 32 && G * (S * 2) <= SE_THREADS && S * 2 <= K) S *= 2;      // slices: power of two, adjacent lanes
+    const int tid = threadIdx.x, g = tid / S, sl = tid - g * S;
+    const bool active = g < G;
 #pragma unroll
-        for (int i = 0; i < SE_IMG; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < SE_IMG; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active) {
         const float4* wp = reinterpret_cast<const float4*>(W) + g;
-        const int n4 = N >> 2;
 #pragma unroll 8
-        for (int k = k0; k < k1; k++) {
-            const float4 w = __ldg(wp + (size_t)k * n4);
+        for (int k = sl; k < K; k += S) {
+            const float4 w = __ldg(wp + (size_t)k * G);
             const float4 x = *reinterpret_cast<const float4*>(v + k * SE_IMG);     // the SE_IMG images' k-th input
             acc[0].x = fmaf(x.x, w.x, acc[0].x); acc[0].y = fmaf(x.x, w.y, acc[0].y); acc[0].z = fmaf(x.x, w.z, acc[0].z); acc[0].w = fmaf(x.x, w.w, acc[0].w);
             acc[1].x = fmaf(x.y, w.x, acc[1].x); acc[1].y = fmaf(x.y, w.y, acc[1].y); acc[1].z = fmaf(x.y, w.z, acc[1].z); acc[1].w = fmaf(x.y, w.w, acc[1].w);
             acc[2].x = fmaf(x.z, w.x, acc[2].x); acc[2].y = fmaf(x.z, w.y, acc[2].y); acc[2].z = fmaf(x.z, w.z, acc[2].z); acc[2].w = fmaf(x.z, w.w, acc[2].w);
             acc[3].x = fmaf(x.w, w.x, acc[3].x); acc[3].y = fmaf(x.w, w.y, acc[3].y); acc[3].z = fmaf(x.w, w.z, acc[3].z); acc[3].w = fmaf(x.w, w.w, acc[3].w);
         }
-#pragma unroll
-        for (int i = 0; i < SE_IMG; i++) reinterpret_cast<float4*>(part + ((size_t)sl * SE_IMG + i) * N)[g] = acc[i];
     }
-    return slices;
+    // S divides 32 and groups start at multiples of S, so a group's slices sit in one warp; idle lanes carry zeros
+    for (int o = S >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < SE_IMG; i++) {
+            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o); acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
+            acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o); acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
+        }
+    }
+    g_out = g;
+    return active && sl == 0;
 }
 
-__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
-                                                    const float* __restrict__ b1, const float* __restrict__ w2,
-                                                    const float* __restrict__ b2, float* __restrict__ scale,
-                                                    int B, int C, int SQ, float inv_hw) {
-    static_assert(SE_IMG == 4, "se_fc_partial reads the 4 images' inputs as one float4");
+__global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
+                                                           const float* __restrict__ b1, const float* __restrict__ w2,
+                                                           const float* __restrict__ b2, float* __restrict__ scale,
+                                                           int B, int C, int SQ, float inv_hw) {
+    static_assert(SE_IMG == 4, "se_fc_layer reads the 4 images' inputs as one float4");
     __shared__ __align__(16) float m[SE_MAXC * SE_IMG];       // [c][image]
     __shared__ __align__(16) float hid[SE_MAXSQ * SE_IMG];    // [j][image]
-    __shared__ __align__(16) float part[SE_PART];             // [slice][image][n]
     const int b0 = blockIdx.x * SE_IMG, tid = threadIdx.x;
-    for (int i = tid; i < C * SE_IMG; i += blockDim.x) {
+    for (int i = tid; i < C * SE_IMG; i += SE_THREADS) {
         const int img = i / C, c = i - img * C;
         m[c * SE_IMG + img] = (b0 + img < B) ? pool[(size_t)(b0 + img) * C + c] * inv_hw : 0.f;
     }
     __syncthreads();
-    const int s1 = se_fc_partial(w1, m, C, SQ, part);
-    __syncthreads();
-    for (int i = tid; i < SQ * SE_IMG; i += blockDim.x) {
-        const int img = i / SQ, j = i - img * SQ;
-        float a = b1[j];
-        for (int sl = 0; sl < s1; sl++) a += part[((size_t)sl * SE_IMG + img) * SQ + j];
-        hid[j * SE_IMG + img] = fmaxf(a, 0.f);
+    float4 acc[SE_IMG]; int g;
+    if (se_fc_layer(w1, m, C, SQ, acc, g)) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b1) + g);
+        const float a[4][4] = {{acc[0].x, acc[0].y, acc[0].z, acc[0].w}, {acc[1].x, acc[1].y, acc[1].z, acc[1].w},
+                               {acc[2].x, acc[2].y, acc[2].z, acc[2].w}, {acc[3].x, acc[3].y, acc[3].z, acc[3].w}};
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int img = 0; img < SE_IMG; img++) hid[(g * 4 + j) * SE_IMG + img] = fmaxf(a[img][j] + bb[j], 0.f);
     }
     __syncthreads();
-    const int s2 = se_fc_partial(w2, hid, SQ, C, part);
-    __syncthreads();
-    for (int i = tid; i < C * SE_IMG; i += blockDim.x) {
-        const int img = i / C, c = i - img * C;
-        if (b0 + img >= B) break;
-        float a = b2[c];
-        for (int sl = 0; sl < s2; sl++) a += part[((size_t)sl * SE_IMG + img) * C + c];
-        scale[(size_t)(b0 + img) * C + c] = apply_act(a, ACT_HSIGMOID);
+    if (se_fc_layer(w2, hid, SQ, C, acc, g)) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(b2) + g);
+#pragma unroll
+        for (int img = 0; img < SE_IMG; img++) {
+            if (b0 + img >= B) break;
+            float4 r;
+            r.x = apply_act(acc[img].x + bv.x, ACT_HSIGMOID); r.y = apply_act(acc[img].y + bv.y, ACT_HSIGMOID);
+            r.z = apply_act(acc[img].z + bv.z, ACT_HSIGMOID); r.w = apply_act(acc[img].w + bv.w, ACT_HSIGMOID);
+            reinterpret_cast<float4*>(scale + (size_t)(b0 + img) * C)[g] = r;
+        }
     }
 }
 
 static int launch_se_fc(const MBBlock& m, const float* pool, float* scale, int B, float inv_hw, cudaStream_t s) {
     if (m.exp > SE_MAXC || m.sq > SE_MAXSQ || (m.exp & 3) || (m.sq & 3)) { set_error("se_fc: unsupported SE shape %d -> %d", m.exp, m.sq); return KPD_ERR_UNSUPPORTED; }
-    se_fc_kernel<<<(B + SE_IMG - 1) / SE_IMG, 256, 0, s>>>(pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
+    se_fc_kernel<<<(B + SE_IMG - 1) / SE_IMG, SE_THREADS, 0, s>>>(pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
     KPD_LAUNCH_CHECK();
     return 0;
 }

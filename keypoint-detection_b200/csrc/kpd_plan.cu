@@ -384,6 +384,7 @@ ScratchMap scratch_map(int B, int S, int n_rois) {
     m.lat3 = take(4 * b * h3 * h3 * 128);
     m.pool_part = take(4 * b * std::max<size_t>(POOL_PARTS, (size_t)S * S / 512) * 128 * 2);   // S*S/512 = 16x8 conv tiles per image
     m.roi_part = take(4 * (size_t)n_rois * ROI_PARTS * 64 * 2);
+    m.att_maps = take(4 * (size_t)n_rois * 2 * 56 * 56);          // head attention: per-pixel mean / max over channels
     m.total = off;
     return m;
 }

@@ -114,25 +114,25 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Head attention (one block per ROI): cw = sigmoid(MLP(avg)+MLP(max)); x*=cw; sw = sigmoid(conv7x7([mean_c,max_c])+b);
-// x*=sw; write the input of deconv_layers[0] as fp32 or bf16 NHWC.
-template <typename OutT>
-__global__ void __launch_bounds__(256) head_attention_kernel(const float* __restrict__ roi_feat, const float* __restrict__ part,
-                                                             const int32_t* __restrict__ roi_count,
-                                                             const float* __restrict__ w0, const float* __restrict__ b0,
-                                                             const float* __restrict__ w2, const float* __restrict__ b2,
-                                                             const float* __restrict__ saw, const float* __restrict__ sab,
-                                                             float* __restrict__ out_cw, float* __restrict__ out_sw,
-                                                             OutT* __restrict__ out, int round_tf32) {
-    const int n = blockIdx.x;
+// Head attention (heatmap_head.py:115-151): cw = sigmoid(MLP(avg)+MLP(max)); x*=cw; sw = sigmoid(conv7x7([mean_c,max_c])+b);
+// x*=sw; the result is the input of deconv_layers[0] (fp32/tf32-rounded or bf16 NHWC).
+// Two kernels, each over (8-row band, ROI) CTAs so that a ROI is spread over 7 CTAs and every access is a 16-byte vector:
+//   head_att_maps_kernel : channel weights (tiny MLP, recomputed per band) and the per-pixel mean/max over channels of x*cw
+//   head_att_apply_kernel: 7x7 spatial attention on the band (+3 halo rows of the maps, zero-padded in shared memory) and
+//                          the scaled output.
+constexpr int HA_ROWS = 8, HA_BANDS = 56 / HA_ROWS, HA_PIX = HA_ROWS * 56;
+
+__global__ void __launch_bounds__(256) head_att_maps_kernel(const float* __restrict__ roi_feat, const float* __restrict__ part,
+                                                            const int32_t* __restrict__ roi_count,
+                                                            const float* __restrict__ w0, const float* __restrict__ b0,
+                                                            const float* __restrict__ w2, const float* __restrict__ b2,
+                                                            float* __restrict__ out_cw, float* __restrict__ maps) {
+    const int n = blockIdx.y, band = blockIdx.x;
     if (n >= *roi_count) return;
     constexpr int HW = 56 * 56;
-    extern __shared__ float smem[];
-    float* mean_map = smem;              // [56*56]
-    float* max_map = smem + HW;          // [56*56]
-    float* sw = smem + 2 * HW;           // [56*56]
-    __shared__ float avg[64], mx[64], cw[64], hid[8], wk[98];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ float avg[64], mx[64], hid[8];
+    __shared__ __align__(16) float cw[64];
+    const int tid = threadIdx.x;
     if (tid < 64) {
         float s = 0.f, m = -INFINITY;
         for (int i = 0; i < ROI_PARTS; i++) {
@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(256) head_attention_kernel(const float* __rest
         }
         avg[tid] = s / (float)HW; mx[tid] = m;
     }
-    if (tid < 98) wk[tid] = saw[tid];
     __syncthreads();
     if (tid < 8) {       // hidden units: 0..3 avg branch, 4..7 max branch
         const int j = tid & 3; const float* v = tid < 4 ? avg : mx;
@@ -155,42 +154,90 @@ __global__ void __launch_bounds__(256) head_attention_kernel(const float* __rest
 #pragma unroll
         for (int j = 0; j < 4; j++) { oa = fmaf(hid[j], w2[tid * 4 + j], oa); om = fmaf(hid[4 + j], w2[tid * 4 + j], om); }
         const float c = 1.f / (1.f + expf(-(oa + om)));
-        cw[tid] = c; out_cw[(int64_t)n * 64 + tid] = c;
+        cw[tid] = c;
+        if (band == 0) out_cw[(int64_t)n * 64 + tid] = c;
     }
     __syncthreads();
-    const float* x = roi_feat + (int64_t)n * HW * 64;
-    const float cw0 = cw[lane], cw1 = cw[lane + 32];
-    for (int p = warp; p < HW; p += 8) {
-        const float v0 = x[(int64_t)p * 64 + lane] * cw0, v1 = x[(int64_t)p * 64 + lane + 32] * cw1;
-        float s = v0 + v1, m = fmaxf(v0, v1);
+    // 16 lanes per pixel (4 channels each), 16 pixels per pass, 4 passes in flight
+    const int l16 = tid & 15, slot = tid >> 4;
+    const float4 c4 = *reinterpret_cast<const float4*>(&cw[l16 * 4]);
+    const float4* x = reinterpret_cast<const float4*>(roi_feat + ((int64_t)n * HW + (int64_t)band * HA_PIX) * 64) + l16;
+    float* mo = maps + (int64_t)n * 2 * HW + band * HA_PIX;
+    for (int p0 = slot; p0 < HA_PIX; p0 += 64) {
+        float4 v[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
-        if (lane == 0) { mean_map[p] = s / 64.f; max_map[p] = m; }
+        for (int u = 0; u < 4; u++) v[u] = __ldg(x + (int64_t)(p0 + 16 * u) * 16);      // HA_PIX = 448 = 7 * 64: no tail
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float a = v[u].x * c4.x, b = v[u].y * c4.y, c = v[u].z * c4.z, d = v[u].w * c4.w;
+            float s = (a + b) + (c + d), m = fmaxf(fmaxf(a, b), fmaxf(c, d));
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+            if (l16 == 0) { mo[p0 + 16 * u] = s / 64.f; mo[HW + p0 + 16 * u] = m; }
+        }
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) head_att_apply_kernel(const float* __restrict__ roi_feat, const float* __restrict__ maps,
+                                                             const int32_t* __restrict__ roi_count, const float* __restrict__ cw_g,
+                                                             const float* __restrict__ saw, const float* __restrict__ sab,
+                                                             float* __restrict__ out_sw, OutT* __restrict__ out, int round_tf32) {
+    const int n = blockIdx.y, band = blockIdx.x;
+    if (n >= *roi_count) return;
+    constexpr int HW = 56 * 56, MR = HA_ROWS + 6, MW = 56 + 6;
+    __shared__ float mmap[2][MR][MW];                       // mean / max maps of the band with a zero-padded 3-pixel halo
+    __shared__ float wk[98], sw[HA_PIX];
+    __shared__ __align__(16) float cw[64];
+    const int tid = threadIdx.x;
+    if (tid < 98) wk[tid] = saw[tid];
+    if (tid < 64) cw[tid] = cw_g[(int64_t)n * 64 + tid];
+    const float* mg = maps + (int64_t)n * 2 * HW;
+    const int r0 = band * HA_ROWS - 3;
+    for (int i = tid; i < 2 * MR * MW; i += 256) {
+        const int ch = i / (MR * MW), rem = i - ch * (MR * MW), ry = rem / MW, rx = rem - ry * MW;
+        const int y = r0 + ry, xx = rx - 3;
+        (&mmap[0][0][0])[i] = (y >= 0 && y < 56 && xx >= 0 && xx < 56) ? mg[ch * HW + y * 56 + xx] : 0.f;
     }
     __syncthreads();
     const float bias = sab[0];
-    for (int p = tid; p < HW; p += 256) {
-        const int y = p / 56, xx = p % 56;
+    for (int p = tid; p < HA_PIX; p += 256) {
+        const int y = p / 56, xx = p - y * 56;
         float a = bias;
-        for (int ky = 0; ky < 7; ky++) {
-            const int iy = y + ky - 3;
-            if (iy < 0 || iy >= 56) continue;
+#pragma unroll
+        for (int ky = 0; ky < 7; ky++)
+#pragma unroll
             for (int kx = 0; kx < 7; kx++) {
-                const int ix = xx + kx - 3;
-                if (ix < 0 || ix >= 56) continue;
-                a = fmaf(mean_map[iy * 56 + ix], wk[ky * 7 + kx], a);
-                a = fmaf(max_map[iy * 56 + ix], wk[49 + ky * 7 + kx], a);
+                a = fmaf(mmap[0][y + ky][xx + kx], wk[ky * 7 + kx], a);
+                a = fmaf(mmap[1][y + ky][xx + kx], wk[49 + ky * 7 + kx], a);
             }
-        }
         const float sv = 1.f / (1.f + expf(-a));
-        sw[p] = sv; out_sw[(int64_t)n * HW + p] = sv;
+        sw[p] = sv; out_sw[(int64_t)n * HW + band * HA_PIX + p] = sv;
     }
     __syncthreads();
-    OutT* o = out + (int64_t)n * HW * 64;
-    for (int64_t e = tid; e < (int64_t)HW * 64; e += 256) {
-        const int c = (int)(e & 63); const int p = (int)(e >> 6);
-        const float v = (x[e] * cw[c]) * sw[p];
-        if constexpr (sizeof(OutT) == 2) o[e] = __float2bfloat16_rn(v); else o[e] = round_tf32 ? tf32_rna(v) : v;
+    const int l16 = tid & 15, slot = tid >> 4;
+    const float4 c4 = *reinterpret_cast<const float4*>(&cw[l16 * 4]);
+    const int64_t base = ((int64_t)n * HW + (int64_t)band * HA_PIX) * 64;
+    const float4* x = reinterpret_cast<const float4*>(roi_feat + base) + l16;
+    for (int p0 = slot; p0 < HA_PIX; p0 += 64) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = __ldg(x + (int64_t)(p0 + 16 * u) * 16);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int p = p0 + 16 * u;
+            const float sv = sw[p];
+            float4 r;
+            r.x = (v[u].x * c4.x) * sv; r.y = (v[u].y * c4.y) * sv; r.z = (v[u].z * c4.z) * sv; r.w = (v[u].w * c4.w) * sv;
+            if constexpr (sizeof(OutT) == 2) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+                uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&lo); pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(out + base + (int64_t)p * 64 + l16 * 4) = pk;
+            } else {
+                if (round_tf32) { r.x = tf32_rna(r.x); r.y = tf32_rna(r.y); r.z = tf32_rna(r.z); r.w = tf32_rna(r.w); }
+                *reinterpret_cast<float4*>(out + base + (int64_t)p * 64 + l16 * 4) = r;
+            }
+        }
     }
 }
 
@@ -216,21 +263,20 @@ int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const 
 int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     ProfScope ps("head_attention", s);
     const ScratchMap sm = scratch_map(B, S, n_max + 1);
-    const size_t dyn = sizeof(float) * 3 * 56 * 56;
     const float* part = reinterpret_cast<const float*>(ws + L.scratch + sm.roi_part);
-    if (out_bf16) {
-        KPD_CUDA(cudaFuncSetAttribute(head_attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        head_attention_kernel<__nv_bfloat16><<<n_max, 256, dyn, s>>>(reinterpret_cast<const float*>(ws + L.roi_feat), part,
-            reinterpret_cast<const int32_t*>(ws + L.roi_count), p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, p->sa_w, p->sa_b,
-            reinterpret_cast<float*>(ws + L.head_cw), reinterpret_cast<float*>(ws + L.head_sw),
-            reinterpret_cast<__nv_bfloat16*>(ws + L.head_in), 0);
-    } else {
-        KPD_CUDA(cudaFuncSetAttribute(head_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        head_attention_kernel<float><<<n_max, 256, dyn, s>>>(reinterpret_cast<const float*>(ws + L.roi_feat), part,
-            reinterpret_cast<const int32_t*>(ws + L.roi_count), p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, p->sa_w, p->sa_b,
-            reinterpret_cast<float*>(ws + L.head_cw), reinterpret_cast<float*>(ws + L.head_sw),
-            reinterpret_cast<float*>(ws + L.head_in), round_tf32);
-    }
+    float* maps = reinterpret_cast<float*>(ws + L.scratch + sm.att_maps);
+    const float* feat = reinterpret_cast<const float*>(ws + L.roi_feat);
+    const int32_t* cnt = reinterpret_cast<const int32_t*>(ws + L.roi_count);
+    float* cw = reinterpret_cast<float*>(ws + L.head_cw);
+    const dim3 grid(HA_BANDS, n_max);
+    head_att_maps_kernel<<<grid, 256, 0, s>>>(feat, part, cnt, p->hca_w0, p->hca_b0, p->hca_w2, p->hca_b2, cw, maps);
+    KPD_LAUNCH_CHECK();
+    if (out_bf16)
+        head_att_apply_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(feat, maps, cnt, cw, p->sa_w, p->sa_b, reinterpret_cast<float*>(ws + L.head_sw),
+                                                                  reinterpret_cast<__nv_bfloat16*>(ws + L.head_in), 0);
+    else
+        head_att_apply_kernel<float><<<grid, 256, 0, s>>>(feat, maps, cnt, cw, p->sa_w, p->sa_b, reinterpret_cast<float*>(ws + L.head_sw),
+                                                          reinterpret_cast<float*>(ws + L.head_in), round_tf32);
     KPD_LAUNCH_CHECK();
     return 0;
 }
