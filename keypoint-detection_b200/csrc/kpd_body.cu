@@ -298,8 +298,8 @@ static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool,
     return 0;
 }
 
-// Batch-wide trunk: every 1x1 conv is one tensor-core GEMM over all B*H*W pixels (3xTF32 mma.sync), every depthwise
-// conv one batch-wide kernel.  At the batch sizes of the benchmark configs the per-image problems (<= 56x56 pixels)
+// Batch-wide trunk: every 1x1 conv is one fp32 GEMM over all B*H*W pixels (CUDA-core FFMA, kpd_pwf.cu; KPD_PW_MMA=1
+// selects the 3xTF32 mma.sync predecessor), every depthwise conv one batch-wide TMA-staged kernel (kpd_dw.cu).  At the batch sizes of the benchmark configs the per-image problems (<= 56x56 pixels)
 // are too small to fill an SM, so the batch-wide form beats the one-cluster-per-image fused kernel (kpd_mbconv.cu);
 // the intermediates (expanded / depthwise tensors) stay L2-resident for B*H*W*C*4 B <= ~100 MB.
 static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
@@ -347,7 +347,8 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
 
 int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     static const bool fused = getenv("KPD_BODY_FUSED") != nullptr;           // one-cluster-per-image fused MBConv kernels
-    if (!strict_fp32 && !fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, ws, L, s); }
+    // default in every precision mode: the batch-wide pipeline is exact fp32 on CUDA cores (FFMA GEMMs, FMA depthwise)
+    if (!fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, ws, L, s); }
     ProfScope ps("body", s);
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
@@ -535,38 +536,24 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
     const int hs[4] = {S / 2, S / 8, S / 16, S / 32};
     const int cin[4] = {16, 24, 48, 576};
     if ((int64_t)B * hs[0] * hs[0] >= (int64_t)1 << 31) { set_error("fpn laterals: B*H*W = %lld pixels exceeds the 32-bit pixel index", (long long)B * hs[0] * hs[0]); return KPD_ERR_UNSUPPORTED; }
-    for (int i = 3; i >= 1 && !strict_fp32; i--) {     // tensor-core laterals 3..1 (3xTF32 GEMM + nearest-upsample add)
+    (void)strict_fp32;                                  // every lateral is exact fp32 on CUDA cores; the modes differ only in round_tf32
+    for (int i = 3; i >= 1; i--) {                       // laterals 3..1: fp32 GEMM + nearest-upsample add in the epilogue
         PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.Wraw = p->w_lat[i]; a.out = lat[i];
         a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
         KPD_TRY(pointwise_mma(a, p->sm_count, s));
     }
-    if (!strict_fp32) {
-        // lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add: CUDA-core streaming kernel (exact fp32, then rounded to tf32
-        // for the FPN-0 MMA).  KPD_LATERAL0_UMMA=1 selects the tcgen05 variant (kind::tf32, 64-byte swizzled K rows, residual
-        // added in the epilogue): measured no faster (its row-per-thread fp32 epilogue stores 512 B/pixel in 16-byte pieces)
-        // and its single-pass tf32 inputs cost score accuracy (1.2e-5 vs 3e-6), so it is not the default.
-        static const bool umma = getenv("KPD_LATERAL0_UMMA") != nullptr;
-        if (umma && hs[0] % 16 == 0) {
-            KPD_TRY(conv_dense_umma(p, p->lat0_conv, 0, ws + L.feat[0], lat[0], 0, B, hs[0], hs[0], ACT_NONE, round_tf32, nullptr, s,
-                                    nullptr, lat[1], hs[0] / hs[1]));
-        } else {
-            KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
-                                    hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
-        }
-    }
-    if (!strict_fp32) return 0;
-    for (int i = 3; i >= 0; i--) {
-        if (i == 0) {
-            KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
-                                    hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
-            break;
-        }
-        PwArgs a{}; a.in = reinterpret_cast<const float*>(ws + L.feat[i]); a.w = p->w_lat[i]; a.bias = nullptr; a.out = lat[i];
-        a.pixels = (int64_t)B * hs[i] * hs[i]; a.cin = cin[i]; a.cout = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
-        if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
-        a.round_tf32 = (i == 0) ? round_tf32 : 0;
-        KPD_TRY(launch_pw(a, s));
+    // lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add: CUDA-core streaming kernel (exact fp32, rounded to tf32 when it
+    // feeds the kind::tf32 FPN-0 MMA).  KPD_LATERAL0_UMMA=1 selects the tcgen05 variant (kind::tf32, 64-byte swizzled K rows,
+    // residual added in the epilogue): measured no faster (its row-per-thread fp32 epilogue stores 512 B/pixel in 16-byte
+    // pieces) and its single-pass tf32 inputs cost score accuracy (1.2e-5 vs 3e-6), so it is not the default.
+    static const bool umma = getenv("KPD_LATERAL0_UMMA") != nullptr;
+    if (umma && !strict_fp32 && hs[0] % 16 == 0) {
+        KPD_TRY(conv_dense_umma(p, p->lat0_conv, 0, ws + L.feat[0], lat[0], 0, B, hs[0], hs[0], ACT_NONE, round_tf32, nullptr, s,
+                                nullptr, lat[1], hs[0] / hs[1]));
+    } else {
+        KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
+                                hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
     }
     return 0;
 }

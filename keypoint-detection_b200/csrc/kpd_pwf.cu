@@ -16,6 +16,7 @@
 // tf32 rounding are fused in the epilogue.
 #include "kpd_common.cuh"
 #include <stdlib.h>
+#include <cmath>
 
 namespace kpd {
 
@@ -171,13 +172,15 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pw_ffma_kernel(const PwMma p, i
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// (R, NT, chunks) per layer: minimise chunks * cover * cycles-per-column of the inner loop (max of the shared-memory
-// wavefronts 8*(4R+NT) and the per-sub-partition issue slots 2*(4*R*NT+R+NT) per 4 k, over the cover of 2R*NT columns).
+// (R, NT, chunks) per layer: minimise chunks * (K/4 * cycles per 4-k step + per-item overhead), the step cost being the
+// larger of the shared-memory wavefronts 8*(4R+NT) and the per-sub-partition issue slots 2*(4*R*NT+R+NT); every extra
+// column chunk re-streams the A tile and pays the item prologue / epilogue again (~1500 issue cycles); items run in waves
+// of two CTAs per SM.
 struct PfCfg { int R, NT, nchunks, chunk_cols; };
-static PfCfg choose_pf_cfg(int N) {
+static PfCfg choose_pf_cfg(int K, int N, int tiles_m, int sm_count) {
     PfCfg best{4, 16, 1, 128};
     double best_cost = 1e30;
-    const int rs[3] = {4, 2, 1}, nts[2] = {16, 8};
+    const int rs[3] = {4, 2, 1}, nts[3] = {16, 12, 8};
     for (int R : rs)
         for (int NT : nts) {
             const int cover = 2 * R * NT;
@@ -185,7 +188,8 @@ static PfCfg choose_pf_cfg(int N) {
             int cc = ((N + nchunks - 1) / nchunks + 3) & ~3;          // even split, float4 granular
             if (cc > cover) cc = cover;
             const double lds = 8.0 * (4 * R + NT), iss = 2.0 * (4 * R * NT + R + NT);
-            const double cost = nchunks * std::max(lds, iss) + 0.02 * nchunks;     // (the cover cancels: cost per pass)
+            const double waves = std::ceil((double)tiles_m * nchunks / (2.0 * sm_count));      // small maps: chunks also buy parallelism
+            const double cost = waves * ((K / 4.0) * std::max(lds, iss) + 1500.0);
             if (cost < best_cost - 1e-9) { best_cost = cost; best = PfCfg{R, NT, nchunks, cc}; }
         }
     return best;
@@ -196,23 +200,27 @@ int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s) {
     if (!p.Wraw) { set_error("pointwise_ffma: missing weights"); return KPD_ERR_ARG; }
     if (p.M <= 0) return 0;
     if (p.M >= ((int64_t)1 << 31) - PF_BM) { set_error("pointwise_ffma: M = %lld pixels exceeds the 32-bit pixel index", (long long)p.M); return KPD_ERR_UNSUPPORTED; }
-    const PfCfg c = choose_pf_cfg(p.N);
     const int tiles_m = (int)((p.M + PF_BM - 1) / PF_BM);
+    const PfCfg c = choose_pf_cfg(p.K, p.N, tiles_m, sm_count);
     const int cover = 2 * c.R * c.NT;
     const size_t smem = sizeof(float) * PF_STAGES * (PF_BM * PF_LDA + PF_KC * cover);
     const int grid = (int)std::min<int64_t>((int64_t)tiles_m * c.nchunks, (int64_t)sm_count * 2);
-    static uint64_t attr[6] = {};
+    static uint64_t attr[9] = {};
 #define KPD_PF_LAUNCH(RR, NN, SLOT)                                                              \
     do {                                                                                         \
         KPD_CUDA(ensure_smem_attr(pw_ffma_kernel<RR, NN>, (int)smem, attr[SLOT]));               \
         pw_ffma_kernel<RR, NN><<<grid, PF_THREADS, smem, s>>>(p, tiles_m, c.nchunks, c.chunk_cols); \
     } while (0)
-    if (c.R == 4 && c.NT == 16) KPD_PF_LAUNCH(4, 16, 0);
-    else if (c.R == 4) KPD_PF_LAUNCH(4, 8, 1);
-    else if (c.R == 2 && c.NT == 16) KPD_PF_LAUNCH(2, 16, 2);
-    else if (c.R == 2) KPD_PF_LAUNCH(2, 8, 3);
-    else if (c.NT == 16) KPD_PF_LAUNCH(1, 16, 4);
-    else KPD_PF_LAUNCH(1, 8, 5);
+#define KPD_PF_NT(RR, BASE)                                                                      \
+    do {                                                                                         \
+        if (c.NT == 16) KPD_PF_LAUNCH(RR, 16, BASE);                                             \
+        else if (c.NT == 12) KPD_PF_LAUNCH(RR, 12, BASE + 1);                                    \
+        else KPD_PF_LAUNCH(RR, 8, BASE + 2);                                                     \
+    } while (0)
+    if (c.R == 4) KPD_PF_NT(4, 0);
+    else if (c.R == 2) KPD_PF_NT(2, 3);
+    else KPD_PF_NT(1, 6);
+#undef KPD_PF_NT
 #undef KPD_PF_LAUNCH
     KPD_LAUNCH_CHECK();
     return 0;
