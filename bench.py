@@ -91,6 +91,42 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+# MobileNetV3-Small inverted-residual table (cin, expanded, cout, stride): the shapes the trunk kernels run on
+MBV3 = [(16, 16, 16, 2), (16, 72, 24, 2), (24, 88, 24, 1), (24, 96, 40, 2), (40, 240, 40, 1), (40, 240, 40, 1),
+        (40, 120, 48, 1), (48, 144, 48, 1), (48, 288, 96, 2), (96, 576, 96, 1), (96, 576, 96, 1)]
+
+
+def trunk_rooflines(kern, B, S, pk, clocks):
+    """Algorithmic bytes / flops of the trunk's kernel classes (layer input + output once per kernel) against the HBM copy
+    peak and the nominal fp32 FMA peak (148 SMs x 128 lanes x 2 flop x the SM clock observed under load)."""
+    out = {}
+    h = S // 2
+    dw_bytes = pw_flops = 0
+    for cin, exp, cout, stride in MBV3:
+        ho = h // stride
+        dw_bytes += 4 * exp * (h * h + ho * ho)
+        if exp != cin:
+            pw_flops += 2 * h * h * cin * exp
+        pw_flops += 2 * ho * ho * exp * cout
+        h = ho
+    pw_flops += 2 * h * h * 96 * 576
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    if "body.depthwise" in kern:
+        out["depthwise (11 TMA-staged kernels; layer in+out bytes)"] = {
+            "achieved_gbs": B * dw_bytes / (kern["body.depthwise"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]}
+    if "body.pointwise" in kern:
+        out["pointwise GEMMs (22 CUDA-core fp32 kernels)"] = {
+            "achieved_tflops": B * pw_flops / (kern["body.pointwise"] * 1e-3) / 1e12, "peak_tflops": fp32_peak,
+            "peak_source": f"nominal fp32 FMA: 148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz"}
+    if "fpn_laterals.lat0" in kern:
+        px = B * (S // 2) ** 2
+        out["lateral0 (1x1 16->128 + x4 top-down add; in+coarse+out bytes)"] = {
+            "achieved_gbs": (px * (64 + 512) + B * (S // 8) ** 2 * 512) / (kern["fpn_laterals.lat0"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]}
+    return out
+
+
+
 def make_inputs(batch, size, persons):
     """Synthetic batch: randn images (the range Normalize(0.5, 0.5) produces), one full-image box per image for
     P=1 (the canonical throughput point) or seeded random boxes for P>1."""
@@ -224,6 +260,11 @@ def main():
         t, n = C.c_double(0), C.c_int64(0)
         if lib.kpd_profile_read(tag.encode(), C.byref(t), C.byref(n)) == 0 and n.value:
             kern[tag] = t.value / n.value
+    # kernel classes inside the trunk scopes: ms per step summed over the class's launches
+    for tag in ("body.stem", "body.pointwise", "body.depthwise", "body.se", "fpn_laterals.lat0"):
+        t, n = C.c_double(0), C.c_int64(0)
+        if lib.kpd_profile_read(tag.encode(), C.byref(t), C.byref(n)) == 0 and n.value:
+            kern[tag] = t.value / prof_steps
     lib.kpd_profile_enable(0)
 
     if rank != 0:
@@ -267,7 +308,14 @@ def main():
                 "body (13 fused kernels, fp32 FMA; algorithmic bytes 0.77 M elem x 4 B per image)": None if "body" not in kern else
                     {"achieved_gbs": B * 0.77e6 * 4 / (kern["body"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]},
                 "decode (fp32 heat maps 17x56x56 per ROI)": None if "decode" not in kern else
-                    {"achieved_gbs": n_roi * (17 * 3136 * 4 + 340) / (kern["decode"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]}},
+                    {"achieved_gbs": n_roi * (17 * 3136 * 4 + 340) / (kern["decode"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]},
+                "roi_align (64 selected channels of the ROI's FPN-0 window in, 56x56x64 fp32 out)": None if "roi_align" not in kern else
+                    {"achieved_gbs": n_roi * (64 * (S // 2) ** 2 * 4 * (1.0 if P == 1 else 0.25) + 3136 * 64 * 4) / (kern["roi_align"] * 1e-3) / 1e9,
+                     "peak_gbs": pk["hbm"], "note": "P=1: the box is the whole map; P>1: seeded boxes cover ~1/4 of the map on average"},
+                "head_attention (56x56x64 fp32 in, head-precision out)": None if "head_attention" not in kern else
+                    {"achieved_gbs": n_roi * 3136 * 64 * (4 + (2 if args.precision == "bf16" else 4)) / (kern["head_attention"] * 1e-3) / 1e9,
+                     "peak_gbs": pk["hbm"]},
+                **trunk_rooflines(kern, B, S, pk, clocks)},
             "model_tflops": value * FLOP_PER_IMAGE / 1e12 / world}
     if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only (task contract)
         line["cpu_baseline"] = cpu_reference(args, args.cpu_baseline_seconds)

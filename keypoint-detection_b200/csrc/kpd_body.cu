@@ -315,6 +315,7 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
     {
         const int64_t total = (int64_t)B * (S / 2) * (S / 2) * 4;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
+        ProfScope ps("body.stem", s);
         stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], B, p->in_channels, S);
         KPD_LAUNCH_CHECK();
     }
@@ -326,22 +327,25 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
         const float* x = cur;
         if (m.w_exp) {
             PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act;
+            ProfScope ps("body.pointwise", s);
             KPD_TRY(pointwise_mma(a, p->sm_count, s));
             x = expand;
         }
         float* pool = nullptr;
         if (m.se) { KPD_CUDA(cudaMemsetAsync(se_pool, 0, sizeof(float) * B * m.exp, s)); pool = se_pool; }
-        KPD_TRY(depthwise_batched(m, x, dwout, pool, B, H, p->sm_count, s));
+        { ProfScope ps("body.depthwise", s); KPD_TRY(depthwise_batched(m, x, dwout, pool, B, H, p->sm_count, s)); }
         if (m.se) {
+            ProfScope ps("body.se", s);
             KPD_TRY(launch_se_fc(m, se_pool, se_scale, B, 1.f / (float)(Ho * Ho), s));
         }
         float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
         PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.Wraw = m.w_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
         a.se_scale = m.se ? se_scale : nullptr; a.hw = Ho * Ho; a.res = m.res ? cur : nullptr; a.res_mode = m.res ? 1 : 0;
-        KPD_TRY(pointwise_mma(a, p->sm_count, s));
+        { ProfScope ps("body.pointwise", s); KPD_TRY(pointwise_mma(a, p->sm_count, s)); }
         cur = dst; H = Ho;
     }
     PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.Wraw = p->w_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH;
+    ProfScope ps("body.pointwise", s);
     return pointwise_mma(a, p->sm_count, s);
 }
 
@@ -552,6 +556,7 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
         KPD_TRY(conv_dense_umma(p, p->lat0_conv, 0, ws + L.feat[0], lat[0], 0, B, hs[0], hs[0], ACT_NONE, round_tf32, nullptr, s,
                                 nullptr, lat[1], hs[0] / hs[1]));
     } else {
+        ProfScope ps0("fpn_laterals.lat0", s);
         KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
                                 hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
     }
