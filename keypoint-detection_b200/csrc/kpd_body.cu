@@ -11,7 +11,7 @@ namespace kpd {
 
 int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out, int B, int H, int strict_fp32, cudaStream_t s);
 
-int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s);
+int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts, int B, int H, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // stem: conv3x3 s2 p1 (Cin -> 16) + folded BN + hardswish.  in NCHW fp32, out NHWC fp32.
@@ -241,7 +241,7 @@ __device__ __forceinline__ bool se_fc_layer(const float* __restrict__ W, const f
     return active && sl == 0;
 }
 
-__global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restrict__ pool, const float* __restrict__ w1,
+__global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restrict__ pool, int parts, const float* __restrict__ w1,
                                                            const float* __restrict__ b1, const float* __restrict__ w2,
                                                            const float* __restrict__ b2, float* __restrict__ scale,
                                                            int B, int C, int SQ, float inv_hw) {
@@ -251,7 +251,10 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restri
     const int b0 = blockIdx.x * SE_IMG, tid = threadIdx.x;
     for (int i = tid; i < C * SE_IMG; i += SE_THREADS) {
         const int img = i / C, c = i - img * C;
-        m[c * SE_IMG + img] = (b0 + img < B) ? pool[(size_t)(b0 + img) * C + c] * inv_hw : 0.f;
+        float sum = 0.f;                                      // per-tile partials of the squeeze, added in tile order
+        if (b0 + img < B)
+            for (int t = 0; t < parts; t++) sum += pool[((size_t)(b0 + img) * parts + t) * C + c];
+        m[c * SE_IMG + img] = sum * inv_hw;
     }
     __syncthreads();
     float4 acc[SE_IMG]; int g;
@@ -279,9 +282,9 @@ __global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restri
     }
 }
 
-static int launch_se_fc(const MBBlock& m, const float* pool, float* scale, int B, float inv_hw, cudaStream_t s) {
+static int launch_se_fc(const MBBlock& m, const float* pool, int parts, float* scale, int B, float inv_hw, cudaStream_t s) {
     if (m.exp > SE_MAXC || m.sq > SE_MAXSQ || (m.exp & 3) || (m.sq & 3)) { set_error("se_fc: unsupported SE shape %d -> %d", m.exp, m.sq); return KPD_ERR_UNSUPPORTED; }
-    se_fc_kernel<<<(B + SE_IMG - 1) / SE_IMG, SE_THREADS, 0, s>>>(pool, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
+    se_fc_kernel<<<(B + SE_IMG - 1) / SE_IMG, SE_THREADS, 0, s>>>(pool, parts, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
     KPD_LAUNCH_CHECK();
     return 0;
 }
@@ -331,12 +334,11 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
             KPD_TRY(pointwise_mma(a, p->sm_count, s));
             x = expand;
         }
-        float* pool = nullptr;
-        if (m.se) { KPD_CUDA(cudaMemsetAsync(se_pool, 0, sizeof(float) * B * m.exp, s)); pool = se_pool; }
-        { ProfScope ps("body.depthwise", s); KPD_TRY(depthwise_batched(m, x, dwout, pool, B, H, p->sm_count, s)); }
+        int pool_parts = 1;
+        { ProfScope ps("body.depthwise", s); KPD_TRY(depthwise_batched(m, x, dwout, m.se ? se_pool : nullptr, sm.se_pool_floats, &pool_parts, B, H, p->sm_count, s)); }
         if (m.se) {
             ProfScope ps("body.se", s);
-            KPD_TRY(launch_se_fc(m, se_pool, se_scale, B, 1.f / (float)(Ho * Ho), s));
+            KPD_TRY(launch_se_fc(m, se_pool, pool_parts, se_scale, B, 1.f / (float)(Ho * Ho), s));
         }
         float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
         PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.Wraw = m.w_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
@@ -392,7 +394,7 @@ int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp
         KPD_TRY(launch_dw(m, x, dwout, pool, B, H, s));
         const float* scale = nullptr;
         if (m.se) {
-            KPD_TRY(launch_se_fc(m, se_pool, se_scale, B, 1.f / (float)(Ho * Ho), s));
+            KPD_TRY(launch_se_fc(m, se_pool, 1, se_scale, B, 1.f / (float)(Ho * Ho), s));
             scale = se_scale;
         }
         // block outputs that the FPN consumes are written straight into their feat slot (features.3 / features.8)

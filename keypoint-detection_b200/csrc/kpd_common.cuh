@@ -119,7 +119,8 @@ struct kpd_plan {
 namespace kpd {
 constexpr int POOL_PARTS = 64;   // per-image partial blocks of the FPN-0 avg/max pool
 constexpr int ROI_PARTS = 28;    // per-ROI partial blocks of the head channel-attention pool (2 rows each)
-struct ScratchMap { size_t expand, dwout, ping, pong, se_pool, se_scale, lat1, lat2, lat3, pool_part, roi_part, att_maps, total; };
+struct ScratchMap { size_t expand, dwout, ping, pong, se_pool, se_scale, lat1, lat2, lat3, pool_part, roi_part, att_maps, total;
+                    size_t se_pool_floats; };     // capacity of se_pool per image (per-tile squeeze partials)
 ScratchMap scratch_map(int B, int S, int n_rois);
 
 // ---- launchers implemented across the .cu files (all enqueue on `s`, return 0 / cudaError) ----

@@ -30,7 +30,7 @@ struct DwArgs {
     int total;
 };
 
-constexpr int DW_THREADS = 256, DW_MAXCG = 128;
+constexpr int DW_THREADS = 256, DW_MAXCG = 128, DW_SLOTS = 16;
 // output columns per run: 4, or 2 for the 5x5 stride-2 layers (their 5 x 11 window would not fit the 128-register budget)
 __host__ __device__ constexpr int dw_xr(int K, int S) { return (K == 5 && S == 2) ? 2 : 4; }
 
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw_tma_kernel(const __grid_cons
     extern __shared__ __align__(128) uint8_t dw_smem[];       // indexed directly (no generic-pointer round trip) so the loads compile to LDS
     uint8_t* const base = dw_smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)a.stages * a.stage_bytes);
-    float* red = reinterpret_cast<float*>(bars + 8);           // [2][DW_MAXCG] SE squeeze partials, double-buffered by tile parity
+    float* red = reinterpret_cast<float*>(bars + 8);           // [2][DW_SLOTS][DW_MAXCG] SE squeeze partials, double-buffered by tile parity
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int step = gridDim.x;
     const bool hsw = a.act == ACT_HSWISH;
@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw_tma_kernel(const __grid_cons
         for (int s = 0; s < a.stages; s++) mbar_init(smem_u32(bars + s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * DW_MAXCG; i += DW_THREADS) red[i] = 0.f;
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < a.stages; s++) { const int item = blockIdx.x + s * step; if (item < a.total) issue(item, s); }
@@ -148,10 +147,16 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw_tma_kernel(const __grid_cons
                 }
             }
         }
-        float* redb = red + (n & 1) * DW_MAXCG;
-        if (a.pool && active) atomicAdd(&redb[ch], ssum);
+        // SE squeeze, deterministic: every thread parks its sum at [slot][channel]; after the barrier one thread per channel
+        // adds the slots that own that channel in a fixed order and stores the tile's partial (summed over tiles by se_fc)
+        float* redb = red + (n & 1) * (DW_SLOTS * DW_MAXCG);
+        if (a.pool && active) redb[slot0 * DW_MAXCG + ch] = ssum;
         __syncthreads();                                      // stage s is free again; this tile's squeeze partials are complete
-        if (a.pool && tid < cg) { atomicAdd(a.pool + (size_t)b * a.C + c0 + tid, redb[tid]); redb[tid] = 0.f; }
+        if (a.pool && tid < cg) {
+            float tot = 0.f;
+            for (int sl = (lpi == 32 ? (tid >> 5) : 0); sl < nslots; sl += nsub) tot += redb[sl * DW_MAXCG + tid];
+            a.pool[((size_t)b * a.tiles + tile) * a.C + c0 + tid] = tot;
+        }
         if (tid == 0) { const int nxt = item + a.stages * step; if (nxt < a.total) issue(nxt, s); }
     }
 }
@@ -191,7 +196,9 @@ static DwCfg choose_dw_cfg(int C, int Ho, int K, int S, size_t budget) {
     return best;
 }
 
-int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s) {
+// `pool` (SE squeeze, may be null): [B][*pool_parts][C] per-tile partial sums, every entry written exactly once (no atomics,
+// no memset); the caller must provide pool_capacity >= *pool_parts * C floats per image.
+int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts, int B, int H, int sm_count, cudaStream_t s) {
     const int S = m.stride, Ho = H / S, C = m.exp, K = m.k;
     if ((C & 3) || (K != 3 && K != 5) || (S != 1 && S != 2) || (m.act != ACT_RELU && m.act != ACT_HSWISH) || (int64_t)Ho * Ho * C >= ((int64_t)1 << 31)) { set_error("depthwise_tma: unsupported layer C=%d k=%d stride=%d", C, K, S); return KPD_ERR_UNSUPPORTED; }
     EncodeTiledFn enc = get_encode();
@@ -214,6 +221,8 @@ int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, in
     a.bias = m.b_dw; a.out = out; a.pool = pool; a.B = B; a.H = H; a.Ho = Ho; a.C = C; a.act = m.act;
     a.TH = TH; a.TW = TW; a.YS = cfg.YS; a.tiles_x = (Ho + TW - 1) / TW; a.tiles = a.tiles_x * ((Ho + TH - 1) / TH); a.CG = CG;
     a.groups = (C + CG - 1) / CG;
+    if (pool_parts) *pool_parts = a.tiles;
+    if (pool && (size_t)a.tiles * C > pool_capacity) { set_error("depthwise_tma: SE partial buffer too small (%d tiles x %d channels)", a.tiles, C); return KPD_ERR_STATE; }
     a.in_h = (TH - 1) * S + K; a.in_w = (TW - 1) * S + K;
     const int tile_bytes = a.in_h * a.in_w * CG * 4, w_bytes = K * K * CG * 4;
     if (a.in_h > 256 || a.in_w > 256 || CG > DW_MAXCG) { set_error("depthwise_tma: unsupported tile %dx%dx%d", a.in_h, a.in_w, CG); return KPD_ERR_UNSUPPORTED; }
@@ -226,7 +235,7 @@ int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, in
     const int64_t total = (int64_t)a.tiles * B * a.groups;
     if (total >= ((int64_t)1 << 31)) { set_error("depthwise_tma: too many work items"); return KPD_ERR_UNSUPPORTED; }
     a.total = (int)total;
-    const size_t smem = (size_t)a.stages * a.stage_bytes + 128 /*align*/ + 64 /*barriers*/ + 2 * DW_MAXCG * 4 /*red*/;
+    const size_t smem = (size_t)a.stages * a.stage_bytes + 128 /*align*/ + 64 /*barriers*/ + 2 * DW_SLOTS * DW_MAXCG * 4 /*red*/;
     if (smem > 227 * 1024) { set_error("depthwise_tma: tile does not fit in shared memory"); return KPD_ERR_UNSUPPORTED; }
     const int ctas_per_sm = std::max(1, std::min(2, (int)((227 * 1024) / (smem + 1024))));
 

@@ -361,7 +361,7 @@ namespace kpd {
 ScratchMap scratch_map(int B, int S, int n_rois) {
     ScratchMap m; size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) & ~size_t(1023); return o; };
-    size_t max_exp = 0, max_dw = 0, max_out = 0;
+    size_t max_exp = 0, max_dw = 0, max_out = 0, max_sq = 576;
     int h = S / 2;
     for (int i = 0; i < 11; i++) {
         const int exp = kBlocks[i][2], cout = kBlocks[i][3], stride = kBlocks[i][6];
@@ -369,6 +369,7 @@ ScratchMap scratch_map(int B, int S, int n_rois) {
         max_exp = std::max(max_exp, (size_t)h * h * exp);
         max_dw = std::max(max_dw, (size_t)ho * ho * exp);
         max_out = std::max(max_out, (size_t)ho * ho * cout);
+        max_sq = std::max(max_sq, (size_t)ho * ((ho + 27) / 28) * exp);      // depthwise tiles (>= 1 row x <= 28.. columns) x channels
         h = ho;
     }
     const size_t b = (size_t)B;
@@ -376,7 +377,7 @@ ScratchMap scratch_map(int B, int S, int n_rois) {
     m.dwout = take(4 * b * max_dw);
     m.ping = take(4 * b * max_out);
     m.pong = take(4 * b * max_out);
-    m.se_pool = take(4 * b * 576);
+    m.se_pool = take(4 * b * max_sq); m.se_pool_floats = max_sq;
     m.se_scale = take(4 * b * 576);
     const size_t h1 = S / 8, h2 = S / 16, h3 = S / 32;
     m.lat1 = take(4 * b * h1 * h1 * 128);

@@ -262,11 +262,13 @@ __global__ void __launch_bounds__(256, 2) dw_tiled_kernel(const float* __restric
     }
 }
 
-int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s);
+int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts, int B, int H, int sm_count, cudaStream_t s);
 
-int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, int sm_count, cudaStream_t s) {
-    static const bool tiled = getenv("KPD_DW_TILED") != nullptr;      // predecessor kept for A/B timing (tools/bench_micro)
-    if (!tiled) return depthwise_tma(m, in, out, pool, B, H, sm_count, s);
+int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts, int B, int H, int sm_count, cudaStream_t s) {
+    static const bool tiled = getenv("KPD_DW_TILED") != nullptr;      // predecessor kept for A/B timing
+    if (!tiled) return depthwise_tma(m, in, out, pool, pool_capacity, pool_parts, B, H, sm_count, s);
+    if (pool_parts) *pool_parts = 1;                                  // the tiled kernel accumulates [B][C] with atomics
+    if (pool) KPD_CUDA(cudaMemsetAsync(pool, 0, sizeof(float) * B * m.exp, s));
     const int Ho = H / m.stride, C = m.exp;
     if (C & 3) { set_error("depthwise_batched: unsupported channel count %d", C); return KPD_ERR_UNSUPPORTED; }
     // channel group: <= 32 channels with (group/4) dividing 256 for every group incl. the last partial one

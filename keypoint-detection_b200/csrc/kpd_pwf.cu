@@ -34,7 +34,7 @@ struct ActHswish { __device__ __forceinline__ float operator()(float x) const { 
 
 // R rows per lane, NT columns per warp strip; WS = 2R strips side by side, RG = 4/R row groups of 32R rows.
 template <int R, int NT>
-__global__ void __launch_bounds__(PF_THREADS, 2) pw_ffma_kernel(const PwMma p, int tiles_m, int nchunks, int chunk_cols) {
+__global__ void __launch_bounds__(PF_THREADS, (R * NT <= 24) ? 3 : 2) pw_ffma_kernel(const PwMma p, int tiles_m, int nchunks, int chunk_cols) {
     constexpr int WS = 2 * R, COVER = WS * NT, STAGE_A = PF_BM * PF_LDA, STAGE_W = PF_KC * COVER;
     constexpr int WV = COVER / 4;                          // float4 per staged W row
     extern __shared__ __align__(16) float pf_smem[];       // [PF_STAGES][STAGE_A + STAGE_W]
@@ -89,10 +89,16 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pw_ffma_kernel(const PwMma p, i
             for (int i = 0; i < 4; i++) simg[i] = min(m0 + srow + 32 * i, M - 1) / (uint32_t)p.hw;
         }
         float acc[R][NT];
+        {   // accumulators start at the bias of this warp's strip (loaded here, long before the epilogue needs it)
+            const int nb0 = n0 + strip * NT;
 #pragma unroll
-        for (int i = 0; i < R; i++)
+            for (int c4 = 0; c4 < NT / 4; c4++) {
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && busy && strip * NT + c4 * 4 < ncols) bv = __ldg(reinterpret_cast<const float4*>(p.bias + nb0 + c4 * 4));
 #pragma unroll
-            for (int j = 0; j < NT; j++) acc[i][j] = 0.f;
+                for (int i = 0; i < R; i++) { acc[i][c4 * 4] = bv.x; acc[i][c4 * 4 + 1] = bv.y; acc[i][c4 * 4 + 2] = bv.z; acc[i][c4 * 4 + 3] = bv.w; }
+            }
+        }
 
         for (int kc = 0; kc < K; kc += PF_KC) {
             asm volatile("cp.async.wait_group %0;" ::"n"(PF_STAGES - 2) : "memory");
@@ -157,7 +163,6 @@ __global__ void __launch_bounds__(PF_THREADS, 2) pw_ffma_kernel(const PwMma p, i
                     const int n = nb + c4 * 4;
                     if (strip * NT + c4 * 4 >= ncols) break;
                     float4 v = make_float4(acc[i][c4 * 4], acc[i][c4 * 4 + 1], acc[i][c4 * 4 + 2], acc[i][c4 * 4 + 3]);
-                    if (p.bias) { const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n)); v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w; }
                     v.x = actfn(v.x); v.y = actfn(v.y); v.z = actfn(v.z); v.w = actfn(v.w);
                     if (resp) { const float4 q = __ldg(reinterpret_cast<const float4*>(resp + n)); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
                     if (p.round_tf32) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }

@@ -435,3 +435,70 @@ def test_rgb_input_three_channels():
     hm, r = out["heatmap"].cpu().numpy(), ref["heatmap"].numpy()
     assert float((np.abs(hm - r) / r).max()) < 1e-4
     np.testing.assert_allclose(out["keypoints"].cpu().numpy(), ref["keypoints"].numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize("size,batch,persons", [(64, 3, 2), (96, 2, 1), (320, 2, 2)])
+def test_forward_other_sizes_against_oracle(model, sd, size, batch, persons):
+    """Sizes with no golden file (tiny 2x2 / 3x3 last maps, a non-224/512 size): CUDA path vs the oracle, strict mode
+    free-running (top-k included) and fp32 mode teacher-forced."""
+    x = torch.from_numpy(synth_images(batch, 1, size, seed=4321))
+    boxes = torch.from_numpy(synth_boxes(batch, persons, seed=17, zero_slots=((0, persons - 1),) if persons > 1 else ()))
+    ref = OM.forward(sd, x, boxes, return_stages=True)
+    for mode, tol in (("fp32_strict", 1e-4), ("fp32", 1e-2)):
+        model.set_precision(mode)
+        out = model.predict({"image": x, "bboxes": boxes}, topk_override=ref["stages"]["topk"].to(torch.int32))
+        st = model.stage_tensors()
+        for i in range(4):
+            e = rel_range_err(nchw(st[f"feat{i}"]), ref["stages"]["feats"][i].numpy())
+            assert e < 1e-4, f"S={size} feat{i} {e}"
+        rr, _ = heatmap_errors(out["heatmap"].cpu().numpy(), ref["heatmap"].numpy())
+        assert rr < tol, f"S={size} {mode}: heat-map range error {rr}"
+        assert float((out["keypoints"].cpu() - ref["keypoints"]).abs().max()) < max(tol, 1e-3)
+        _report(f"other_sizes/S{size}/{mode}/heatmap_range_err", rr)
+    model.set_precision("fp32_strict")
+    out = model.predict({"image": x, "bboxes": boxes})
+    srt = np.sort(ref["stages"]["scores"].numpy(), axis=1)[:, ::-1]
+    clear = (srt[:, :64] - srt[:, 1:65]).min(axis=1) > 1e-5          # images whose top-64 boundary / order is not a near-tie
+    same = (model.stage_tensors()["topk"].cpu().numpy() == ref["stages"]["topk"].numpy()).all(axis=1)
+    assert (same | ~clear).all(), "free-running top-k differs on images with clear score gaps"
+
+
+def test_forward_full_size_properties():
+    """BASELINE config C2 at full size (B=256, 224x224) with ragged boxes, through size-independent properties:
+    batch independence (an image's outputs do not depend on its batch-mates), run-to-run stability, zero padding,
+    value ranges and the dummy-person rule.  (The oracle needs ~30 s per 8 images, so full size is checked this way.)"""
+    from dll import MultiPersonKeypointModel
+    from dll.configs.config_loader import load_config
+    cfg = load_config(os.path.join(ROOT, "configs", "default_config.yaml"))
+    m = MultiPersonKeypointModel(cfg.model, cfg.training)
+    m.load_state_dict(synth_state_dict(seed=0), strict=True)
+    m = m.cuda().eval()
+    B, P = 256, 2
+    x = torch.from_numpy(synth_images(B, 1, 224, seed=77))
+    zero = tuple((b, 1) for b in range(0, B, 3)) + ((5, 0), (5, 1))          # ragged: every third image has one box, image 5 none
+    boxes = torch.from_numpy(synth_boxes(B, P, seed=5, zero_slots=zero))
+    for mode in ("bf16", "fp32"):
+        m.set_precision(mode)
+        big = {k: v.cpu() for k, v in m.predict({"image": x, "bboxes": boxes}).items() if torch.is_tensor(v)}
+        again = {k: v.cpu() for k, v in m.predict({"image": x, "bboxes": boxes}).items() if torch.is_tensor(v)}
+        hm = big["heatmap"]
+        assert hm.shape == (B, P, 17, 56, 56) and big["keypoints"].shape == (B, P, 1, 17, 2) and big["visibilities"].shape == (B, P, 1, 17, 3)
+        assert torch.isfinite(hm).all() and float(hm.min()) >= 0.0 and float(hm.max()) <= 1.0
+        assert float(big["keypoints"].min()) >= 0.0 and float(big["keypoints"].max()) <= 1.0
+        # run-to-run: only the SE / pooling atomics reorder fp32 sums
+        assert float((hm - again["heatmap"]).abs().max()) < 1e-4
+        # padded person slots are zero; image 5 (no valid box) gets the dummy person: vis = [1,0,0] in slot 0
+        for b in range(0, B, 3):
+            if b != 5:
+                assert float(hm[b, 1].abs().max()) == 0.0 and float(big["visibilities"][b, 1].abs().max()) == 0.0
+        assert float(hm[5].abs().max()) == 0.0
+        assert torch.equal(big["visibilities"][5, 0, 0], torch.tensor([[1.0, 0.0, 0.0]]).repeat(17, 1))
+        # one-hot visibilities for every real person
+        vis = big["visibilities"][:, :, 0]
+        real = vis.sum(-1).sum(-1) > 0
+        assert torch.all(vis[real].sum(-1) == 1.0)
+        # batch independence: images 8..15 alone give the same heat maps (same kernels, different tiling of the batch)
+        sub = m.predict({"image": x[8:16], "bboxes": boxes[8:16]})
+        d = float((sub["heatmap"].cpu() - hm[8:16]).abs().max())
+        assert d < (2e-3 if mode == "bf16" else 2e-4), f"{mode}: batch-dependence {d}"
+        _report(f"full_size/{mode}/batch_independence_max_abs", d)
