@@ -1,6 +1,7 @@
 // extern "C" forward entry points: orchestration of the hot path on the caller's stream.
 //   reference: dll/models/keypoint_model.py:73-206 (MultiPersonKeypointModel.forward with bboxes supplied).
 #include "kpd_common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace kpd {
@@ -145,12 +146,25 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     const kpd_workspace_layout& L = *layout;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
-    KPD_TRY(run_body(plan, d_images, B, S, precision == KPD_PREC_FP32_SIMT, ws, L, s));
-    KPD_TRY(run_fpn_laterals(plan, B, S, precision != KPD_PREC_FP32_SIMT, precision == KPD_PREC_FP32_SIMT, ws, L, s));
+    // FPN level 0: composed tcgen05 form (kpd_fpn0.cu; lateral 0 never materialised) unless strict fp32 or KPD_FPN0_CLASSIC=1
+    static const bool classic = getenv("KPD_FPN0_CLASSIC") != nullptr;
+    const bool strict = precision == KPD_PREC_FP32_SIMT;
+    const bool composed = !strict && !classic;
+    KPD_TRY(run_body(plan, d_images, B, S, strict, composed, ws, L, s));
+    KPD_TRY(run_fpn_laterals(plan, B, S, !strict, strict, composed, ws, L, s));
     const ScratchMap sm = scratch_map(B, S, 1);
     float* pool_part = reinterpret_cast<float*>(ws + L.scratch + sm.pool_part);
     const int H0 = S / 2;
-    const bool fuse_pool = precision != KPD_PREC_FP32_SIMT && (H0 % 16 == 0) && (H0 % 8 == 0);
+    if (composed) {
+        {
+            ProfScope ps("fpn0_conv", s);
+            KPD_TRY(fpn0_fused(plan, reinterpret_cast<const float*>(ws + L.scratch + sm.f0_tf32), reinterpret_cast<const float*>(ws + L.scratch + sm.lat1),
+                               reinterpret_cast<float*>(ws + L.fpn0), pool_part, B, S, s));
+        }
+        KPD_TRY(run_pool_final(pool_part, B, fpn0_fused_parts(S), H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg), reinterpret_cast<float*>(ws + L.pool_max), s));
+        return 0;
+    }
+    const bool fuse_pool = !strict && (H0 % 16 == 0) && (H0 % 8 == 0);
     {
         ProfScope ps("fpn0_conv", s);
         if (fuse_pool)      // avg/max pooling for the channel scores is reduced in the conv epilogue (fp32 accumulators)

@@ -18,7 +18,7 @@ int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool
 // 4 threads per output pixel, each 4 output channels -> one coalesced float4 store per thread.
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ out,
-                                                   int B, int Cin, int S) {
+                                                   float* __restrict__ out_tf32, int B, int Cin, int S) {
     __shared__ float ws[27 * 16];
     __shared__ float bs[16];
     for (int i = threadIdx.x; i < 9 * Cin * 16; i += blockDim.x) ws[i] = w[i];
@@ -51,6 +51,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
         r.x = apply_act(a0 + bs[q * 4 + 0], ACT_HSWISH); r.y = apply_act(a1 + bs[q * 4 + 1], ACT_HSWISH);
         r.z = apply_act(a2 + bs[q * 4 + 2], ACT_HSWISH); r.w = apply_act(a3 + bs[q * 4 + 3], ACT_HSWISH);
         reinterpret_cast<float4*>(out)[t] = r;
+        if (out_tf32) {                                     // second copy rounded to tf32: the A operand of the composed FPN-0 conv (kpd_fpn0.cu)
+            r.x = tf32_rna(r.x); r.y = tf32_rna(r.y); r.z = tf32_rna(r.z); r.w = tf32_rna(r.w);
+            reinterpret_cast<float4*>(out_tf32)[t] = r;
+        }
     }
 }
 
@@ -305,9 +309,10 @@ static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool,
 // selects the 3xTF32 mma.sync predecessor), every depthwise conv one batch-wide TMA-staged kernel (kpd_dw.cu).  At the batch sizes of the benchmark configs the per-image problems (<= 56x56 pixels)
 // are too small to fill an SM, so the batch-wide form beats the one-cluster-per-image fused kernel (kpd_mbconv.cu);
 // the intermediates (expanded / depthwise tensors) stay L2-resident for B*H*W*C*4 B <= ~100 MB.
-static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
+    float* f0_tf32 = want_f0_tf32 ? reinterpret_cast<float*>(scratch + sm.f0_tf32) : nullptr;
     float* feat[4]; for (int i = 0; i < 4; i++) feat[i] = reinterpret_cast<float*>(ws + L.feat[i]);
     float* expand = reinterpret_cast<float*>(scratch + sm.expand);
     float* dwout = reinterpret_cast<float*>(scratch + sm.dwout);
@@ -319,7 +324,7 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
         const int64_t total = (int64_t)B * (S / 2) * (S / 2) * 4;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
         ProfScope ps("body.stem", s);
-        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], B, p->in_channels, S);
+        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], f0_tf32, B, p->in_channels, S);
         KPD_LAUNCH_CHECK();
     }
     const float* cur = feat[0];
@@ -351,13 +356,14 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
     return pointwise_mma(a, p->sm_count, s);
 }
 
-int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     static const bool fused = getenv("KPD_BODY_FUSED") != nullptr;           // one-cluster-per-image fused MBConv kernels
     // default in every precision mode: the batch-wide pipeline is exact fp32 on CUDA cores (FFMA GEMMs, FMA depthwise)
-    if (!fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, ws, L, s); }
+    if (!fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, want_f0_tf32, ws, L, s); }
     ProfScope ps("body", s);
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
+    float* f0_tf32 = want_f0_tf32 ? reinterpret_cast<float*>(scratch + sm.f0_tf32) : nullptr;
     float* feat[4]; for (int i = 0; i < 4; i++) feat[i] = reinterpret_cast<float*>(ws + L.feat[i]);
     float* expand = reinterpret_cast<float*>(scratch + sm.expand);
     float* dwout = reinterpret_cast<float*>(scratch + sm.dwout);
@@ -369,7 +375,7 @@ int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp
     {
         const int64_t total = (int64_t)B * (S / 2) * (S / 2) * 4;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
-        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], B, p->in_channels, S);
+        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], f0_tf32, B, p->in_channels, S);
         KPD_LAUNCH_CHECK();
     }
     const float* cur = feat[0];
@@ -533,7 +539,8 @@ static int launch_lateral0(const float* feat0, const float* w, const float* coar
 
 // FPN laterals + top-down pathway (backbone.py:33-37): lat3 = L3(f3); lat2 = L2(f2)+up2(lat3); lat1 = L1(f1)+up2(lat2);
 // lateral0 = L0(f0) + up4(lat1)  -> written to the workspace as the input of fpn_convs[0].
-int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+// composed != 0: FPN-0 runs in composed form (kpd_fpn0.cu) -- lateral 0 is not materialised and lateral 1 is rounded to tf32
+int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, int composed, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     ProfScope ps("fpn_laterals", s);
     const ScratchMap sm = scratch_map(B, S, 1);
     char* scratch = ws + L.scratch;
@@ -547,8 +554,10 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
         PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.Wraw = p->w_lat[i]; a.out = lat[i];
         a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
+        a.round_tf32 = (composed && i == 1) ? 1 : 0;
         KPD_TRY(pointwise_mma(a, p->sm_count, s));
     }
+    if (composed) return 0;
     // lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add: CUDA-core streaming kernel (exact fp32, rounded to tf32 when it
     // feeds the kind::tf32 FPN-0 MMA).  KPD_LATERAL0_UMMA=1 selects the tcgen05 variant (kind::tf32, 64-byte swizzled K rows,
     // residual added in the epilogue): measured no faster (its row-per-thread fp32 epilogue stores 512 B/pixel in 16-byte

@@ -104,6 +104,9 @@ struct kpd_plan {
     const float* w_lat[4];                        // [cin_i][128]
     const float4* wf_lat[4];                      // laterals as 3xTF32 mma fragments
     kpd::DenseConv lat0_conv;                     // lateral 0 (1x1, 16 -> 128) packed for the tcgen05 kernel (64-byte K rows)
+    // FPN-0 in composed form (kpd_fpn0.cu): conv3x3(L0 f0 + up4(lat1)) = conv3x3_{W1}(f0) + sum over coarse neighbours W2 lat1
+    const float* fpn0c_w1;                        // [128 cout][9 taps * 16 cin] tf32: fpn_convs[0] (BN folded) composed with lateral_convs[0]
+    const float* fpn0c_w2;                        // [36][128 cout][128 cin] tf32: per sub-position / coarse-neighbour sums of the 3x3 taps
     kpd::DenseConv fpn_conv[4];
     // channel attention (model level): fc0 [8][128]+[8], fc2 [128][8]+[128]
     const float *ca_w0, *ca_b0, *ca_w2, *ca_b2;
@@ -119,13 +122,15 @@ struct kpd_plan {
 namespace kpd {
 constexpr int POOL_PARTS = 64;   // per-image partial blocks of the FPN-0 avg/max pool
 constexpr int ROI_PARTS = 28;    // per-ROI partial blocks of the head channel-attention pool (2 rows each)
-struct ScratchMap { size_t expand, dwout, ping, pong, se_pool, se_scale, lat1, lat2, lat3, pool_part, roi_part, att_maps, total;
+struct ScratchMap { size_t expand, dwout, ping, pong, se_pool, se_scale, f0_tf32, lat1, lat2, lat3, pool_part, roi_part, att_maps, total;
                     size_t se_pool_floats; };     // capacity of se_pool per image (per-tile squeeze partials)
 ScratchMap scratch_map(int B, int S, int n_rois);
 
 // ---- launchers implemented across the .cu files (all enqueue on `s`, return 0 / cudaError) ----
-int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, int composed, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, float* out, float* pool_part, int B, int S, cudaStream_t s);
+int fpn0_fused_parts(int S);
 int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* scratch, cudaStream_t s);
 int run_pool_final(const float* partials, int B, int parts, int HW, float* avg, float* mx, cudaStream_t s);
 int run_scores_topk(const kpd_plan* p, int B, const float* avg, const float* mx, float* scores, int32_t* topk, cudaStream_t s);

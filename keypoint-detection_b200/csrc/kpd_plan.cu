@@ -270,6 +270,42 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
     for (int i = 0; i < 4; i++) {
         const float* w = c.next(); BN bn = read_bn(c);
         dense(p->fpn_conv[i], w, nullptr, &bn, EPS_HEAD, 128, 128, 3);
+        if (i == 0) {
+            // composed FPN-0 weights (kpd_fpn0.cu).  lateral0 = L0 f0 + up4(lat1) is never materialised:
+            //   W1[o][tap][i] = sum_c Wc[o][c][tap] * L0[c][i]      (3x3 conv straight from the 16-channel stem output)
+            //   W2[m][o][c]   = sum of the taps of Wc that read coarse neighbour (ny,nx) from sub-position (py,px) of a 4x4 block
+            // m enumerates (py, px, ny, nx) in that nesting order over the non-empty neighbours (36 in total).
+            std::vector<double> sc(128, 1.0), sh(128, 0.0);
+            bn_affine(bn, 128, EPS_HEAD, sc, sh);
+            const size_t o1 = B.alloc(sizeof(float) * 128 * 144), o2 = B.alloc(sizeof(float) * 36 * 128 * 128);
+            for (int o = 0; o < 128; o++)
+                for (int t = 0; t < 9; t++)
+                    for (int ci = 0; ci < 16; ci++) {
+                        double a = 0.0;
+                        for (int cc = 0; cc < 128; cc++) a += (double)w[((size_t)o * 128 + cc) * 9 + t] * (double)w_lat0_raw[cc * 16 + ci];
+                        B.f(o1)[(size_t)o * 144 + t * 16 + ci] = to_tf32((float)(a * sc[o]));
+                    }
+            auto nbr = [](int pp, int d) { const int q = pp + d; return q < 0 ? -1 : (q > 3 ? 1 : 0); };
+            int m = 0;
+            for (int py = 0; py < 4; py++)
+                for (int px = 0; px < 4; px++)
+                    for (int ny = -1; ny <= 1; ny++)
+                        for (int nx = -1; nx <= 1; nx++) {
+                            bool any = false;
+                            for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) if (nbr(py, dy) == ny && nbr(px, dx) == nx) any = true;
+                            if (!any) continue;
+                            for (int o = 0; o < 128; o++)
+                                for (int cc = 0; cc < 128; cc++) {
+                                    double a = 0.0;
+                                    for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++)
+                                        if (nbr(py, dy) == ny && nbr(px, dx) == nx) a += (double)w[((size_t)o * 128 + cc) * 9 + (dy + 1) * 3 + (dx + 1)];
+                                    B.f(o2)[((size_t)m * 128 + o) * 128 + cc] = to_tf32((float)(a * sc[o]));
+                                }
+                            m++;
+                        }
+            if (m != 36) { set_error("internal: composed FPN-0 weight count %d != 36", m); delete p; return KPD_ERR_STATE; }
+            reg(&p->fpn0c_w1, o1); reg(&p->fpn0c_w2, o2);
+        }
     }
     c.skip();   // person_detector.anchors (never read by the reference forward, person_head.py:141-166)
     for (int i = 0; i < 4; i++) {
@@ -380,10 +416,11 @@ ScratchMap scratch_map(int B, int S, int n_rois) {
     m.se_pool = take(4 * b * max_sq); m.se_pool_floats = max_sq;
     m.se_scale = take(4 * b * 576);
     const size_t h1 = S / 8, h2 = S / 16, h3 = S / 32;
-    m.lat1 = take(4 * b * h1 * h1 * 128);
+    m.f0_tf32 = take(4 * (b + 1) * (size_t)(S / 2) * (S / 2) * 16);     // tf32 copy of the stem output (+1 image: pair-wide TMA boxes)
+    m.lat1 = take(4 * (b + 1) * h1 * h1 * 128);
     m.lat2 = take(4 * b * h2 * h2 * 128);
     m.lat3 = take(4 * b * h3 * h3 * 128);
-    m.pool_part = take(4 * b * std::max<size_t>(POOL_PARTS, (size_t)S * S / 512) * 128 * 2);   // S*S/512 = 16x8 conv tiles per image
+    m.pool_part = take(4 * b * std::max<size_t>(std::max<size_t>(POOL_PARTS, (size_t)S * S / 512), (size_t)fpn0_fused_parts(S)) * 128 * 2);   // conv tiles per image
     m.roi_part = take(4 * (size_t)n_rois * ROI_PARTS * 64 * 2);
     m.att_maps = take(4 * (size_t)n_rois * 2 * 56 * 56);          // head attention: per-pixel mean / max over channels
     m.total = off;
