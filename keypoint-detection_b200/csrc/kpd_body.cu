@@ -51,9 +51,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ in,
         r.x = apply_act(a0 + bs[q * 4 + 0], ACT_HSWISH); r.y = apply_act(a1 + bs[q * 4 + 1], ACT_HSWISH);
         r.z = apply_act(a2 + bs[q * 4 + 2], ACT_HSWISH); r.w = apply_act(a3 + bs[q * 4 + 3], ACT_HSWISH);
         reinterpret_cast<float4*>(out)[t] = r;
-        if (out_tf32) {                                     // second copy rounded to tf32: the A operand of the composed FPN-0 conv (kpd_fpn0.cu)
+        if (out_tf32) {     // second copy, rounded to tf32 and stored as 16 sub-position planes [oy&3][ox&3][image][Ho/4][Ho/4][16]:
+                            // the A operand of the composed FPN-0 conv (kpd_fpn0.cu)
             r.x = tf32_rna(r.x); r.y = tf32_rna(r.y); r.z = tf32_rna(r.z); r.w = tf32_rna(r.w);
-            reinterpret_cast<float4*>(out_tf32)[t] = r;
+            const uint32_t Hc = Ho >> 2, NBi = ((uint32_t)B + 1u) & ~1u;
+            const uint32_t plane = (uint32_t)(oy & 3) * 4 + (uint32_t)(ox & 3);
+            const size_t pixel = (((size_t)plane * NBi + (uint32_t)b) * Hc + (uint32_t)(oy >> 2)) * Hc + (uint32_t)(ox >> 2);
+            reinterpret_cast<float4*>(out_tf32)[pixel * 4 + q] = r;
         }
     }
 }

@@ -13,8 +13,9 @@
 // disappear.  Zero padding is preserved: taps outside the image read TMA out-of-bounds zeros in both forms.
 //
 // GEMM tiling: rows of an M=128 tile are the pixels {2 images} x {4 coarse rows} x {16 coarse columns} at ONE sub-position
-// (py,px), i.e. output pixels (4cy+py, 4cx+px); all rows then share the B operand.  (A) loads them with a TMA traversal
-// stride of 4 in x and y (box {16 ch, 64, 16, 2}, elementStrides {1,4,4,1}, 64-byte swizzled rows); (B) loads the coarse
+// (py,px), i.e. output pixels (4cy+py, 4cx+px); all rows then share the B operand.  For (A) the stem writes a tf32 copy of f0
+// as 16 sub-position planes (space-to-depth by 4), so a tap's pixels are a dense box {16 ch, 16, 4, 2} of one plane (64-byte
+// swizzled rows; a stride-4 TMA traversal of the plain layout works too but is request-bound); (B) loads the coarse
 // neighbour tile as a plain box {32 ch, 16, 4, 2} (128-byte swizzled rows) 4 K-slabs per neighbour.  Two tiles (adjacent
 // coarse column blocks) share every weight stage.  Warp roles, mbarrier rings and the TMEM double buffer are those of
 // conv_umma_kernel (kpd_conv_umma.cu).
@@ -24,14 +25,15 @@
 namespace kpd {
 
 struct Fpn0Params {
-    int B, H0, W0, Hc, Wc;             // fine map H0 x W0 = 4 Hc x 4 Wc
+    int B, NB, H0, W0, Hc, Wc;         // fine map H0 x W0 = 4 Hc x 4 Wc; NB = B rounded up to even (image extent of the TMA maps)
     int tiles_cx, tiles_cy, cxgroups;  // coarse tiles of 16 x 4; cxgroups = pairs of column tiles sharing weights
     int stages, total_groups, parts;   // parts = pooling partials per image = tiles_cy * tiles_cx * 16
     int mat_base[16];                  // first W2 matrix of sub-position sp = py*4 + px
     const float* bias; float* out; float* pool_part;
+    int skip;                          // timing attribution only (KPD_FPN0_SKIP): 1 no part (A), 2 no part (B), 4 no output stores, 8 no pooling
 };
 
-constexpr int F0_THREADS = 192, F0_MT = 2, F0_SLOT = 16384, F0_STAGE = (F0_MT + 1) * F0_SLOT;
+constexpr int F0_EPI_WARPS = 8 /* 4 per tile of a group */, F0_RS = 36 /* padded row of the epilogue transpose tile */, F0_THREADS = 64 + 32 * F0_EPI_WARPS, F0_MT = 2, F0_SLOT = 16384, F0_STAGE = (F0_MT + 1) * F0_SLOT;
 
 __device__ __forceinline__ int f0_first(int p) { return p == 0 ? -1 : 0; }            // first coarse-neighbour offset along an axis
 __device__ __forceinline__ int f0_count(int p) { return (p == 0 || p == 3) ? 2 : 1; }   // neighbours along an axis
@@ -45,8 +47,8 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * F0_STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
-    float* red = sbias + 128;                          // [4 warps][32][33] transpose tiles
-    float* wred = red + 4 * 32 * 33;                   // [4 warps][2][128] per-warp channel sum / max
+    float* red = sbias + 128;                          // [4 warps][32][F0_RS] transpose tiles (16-byte aligned rows)
+    float* wred = red + F0_EPI_WARPS * 32 * F0_RS;        // [2 tiles][4 lane groups][2][128] channel sum / max over a lane group's 32 rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -62,7 +64,7 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW1) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW2) : "memory");
         for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), F0_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 128; i += blockDim.x) sbias[i] = p.bias[i];
@@ -89,21 +91,27 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
             for (int grp = blockIdx.x; grp < p.total_groups; grp += gridDim.x) {
                 int sp, cxg, cyt, pair; decode(grp, sp, cxg, cyt, pair);
                 const int py = sp >> 2, px = sp & 3, n0 = pair * 2, cy0 = cyt * 4, cx0 = cxg * (F0_MT * 16);
-                // (A) 9 taps of the composed 16-channel conv: strided pixel box of f0, 64-byte rows
-                int dy = -1, dx = -1;
-                for (int tap = 0; tap < 9; tap++) {
+                // (A) 9 taps of the composed 16-channel conv, two taps per stage.  f0 is stored as 16 sub-position planes
+                // [qy*4+qx][image][Hc][Wc][16] (space-to-depth by 4), so the pixels (4cy+py+dy, 4cx+px+dx) of a tile are a DENSE box
+                // of plane ((py+dy)&3, (px+dx)&3) shifted by the coarse carry -- 1 KB contiguous per box row instead of a stride-4 gather
+                for (int t0 = (p.skip & 1) ? 8 : 0; t0 < 9; t0 += 2) {
+                    const int nt = min(2, 9 - t0);
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_expect_tx(full_bar(stage), (uint32_t)((F0_MT + 1) * 8192));
+                    mbar_expect_tx(full_bar(stage), (uint32_t)(nt * (F0_MT + 1) * 8192));
                     const uint32_t sa = smem_u32(smem + (size_t)stage * F0_STAGE);
+                    for (int t = 0; t < nt; t++) {
+                        const int tap = t0 + t, ty = py + tap / 3 - 1, tx = px + tap % 3 - 1;
+                        const int plane = (ty & 3) * 4 + (tx & 3);
+                        const int ny = ty < 0 ? -1 : (ty > 3 ? 1 : 0), nx = tx < 0 ? -1 : (tx > 3 ? 1 : 0);
 #pragma unroll
-                    for (int i = 0; i < F0_MT; i++)
-                        tma_load_4d(sa + i * F0_SLOT, &tmF, full_bar(stage), 0, 4 * (cx0 + 16 * i) + px + dx, 4 * cy0 + py + dy, n0);
-                    tma_load_2d(sa + F0_MT * F0_SLOT, &tmW1, full_bar(stage), tap * 16, 0);
-                    if (++dx == 2) { dx = -1; dy++; }
+                        for (int i = 0; i < F0_MT; i++)
+                            tma_load_4d(sa + i * F0_SLOT + t * 8192, &tmF, full_bar(stage), 0, cx0 + 16 * i + nx, cy0 + ny, plane * p.NB + n0);
+                        tma_load_2d(sa + F0_MT * F0_SLOT + t * 8192, &tmW1, full_bar(stage), tap * 16, 0);
+                    }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
                 // (B) the coarse neighbours of this sub-position: 4 K-slabs of 32 channels each, 128-byte rows
-                const int fy = f0_first(py), fx = f0_first(px), ncx = f0_count(px), nb = f0_count(py) * ncx;
+                const int fy = f0_first(py), fx = f0_first(px), ncx = f0_count(px), nb = (p.skip & 2) ? 0 : f0_count(py) * ncx;
                 for (int j = 0; j < nb; j++) {
                     const int ny = fy + j / ncx, nx = fx + j % ncx, mat = p.mat_base[sp] + j;
 #pragma unroll
@@ -127,21 +135,24 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int grp = blockIdx.x; grp < p.total_groups; grp += gridDim.x) {
                 const int sp = grp & 15;
-                const int nb = f0_count(sp >> 2) * f0_count(sp & 3);
+                const int nb = (p.skip & 2) ? 0 : f0_count(sp >> 2) * f0_count(sp & 3);
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * F0_MT * 128);
-                for (int tap = 0; tap < 9; tap++) {                     // (A): 64-byte rows, 2 K steps of 8 floats
+                for (int t0 = (p.skip & 1) ? 8 : 0; t0 < 9; t0 += 2) {  // (A): two taps per stage, 64-byte rows, 2 K steps of 8 floats each
+                    const int nt = min(2, 9 - t0);
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * F0_STAGE);
-                    const uint64_t bdesc = make_sdesc_rb(sa + F0_MT * F0_SLOT, 64);
+                    for (int t = 0; t < nt; t++) {
+                        const uint64_t bdesc = make_sdesc_rb(sa + F0_MT * F0_SLOT + t * 8192, 64);
 #pragma unroll
-                    for (int i = 0; i < F0_MT; i++) {
-                        const uint64_t adesc = make_sdesc_rb(sa + i * F0_SLOT, 64);
+                        for (int i = 0; i < F0_MT; i++) {
+                            const uint64_t adesc = make_sdesc_rb(sa + i * F0_SLOT + t * 8192, 64);
 #pragma unroll
-                        for (int k4 = 0; k4 < 2; k4++)
-                            tc_mma<false>(d_tmem + (uint32_t)(i * 128), adesc + 2 * k4, bdesc + 2 * k4, idesc, (tap | k4) != 0 ? 1u : 0u);
+                            for (int k4 = 0; k4 < 2; k4++)
+                                tc_mma<false>(d_tmem + (uint32_t)(i * 128), adesc + 2 * k4, bdesc + 2 * k4, idesc, ((p.skip & 1) ? k4 : (t0 | t | k4)) != 0 ? 1u : 0u);
+                        }
                     }
                     tc_commit(empty_bar(stage));
                     if (++stage == S) { stage = 0; phase ^= 1; }
@@ -165,8 +176,11 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else {                                            // ---------------- epilogue warps 2..5
+    } else {                                            // ---------------- epilogue: warps 2..5 take tile 0 of a group, warps 6..9 tile 1
+        // (one warp per tile row block is a ~900-cycle dependent chain per 32-channel chunk -- tcgen05.ld, bias/ReLU, transpose,
+        // stores, pooling -- so the two tiles of a group are drained side by side; measured 0.63 -> 0.35 ms of fixed cost)
         const int lg = warp & 3;                        // TMEM lane group this warp may access
+        const int ti = (warp - 2) >> 2;                 // which tile of the group
         const int row = lg * 32 + lane;
         const int cxl = row & 15, cyl = (row >> 4) & 3, nl = row >> 6;      // TMA box order: column fastest, then row, then image
         int acc = 0; uint32_t acc_phase = 0;
@@ -175,52 +189,80 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
             const int py = sp >> 2, px = sp & 3;
             mbar_wait_warp(tfull_bar(acc), acc_phase, lane);
             tc_fence_after();
-            for (int ti = 0; ti < F0_MT; ti++) {
+            {
                 const int cxt = cxg * F0_MT + ti;
-                if (cxt >= p.tiles_cx) break;
+                if (cxt < p.tiles_cx) {
                 const int cx = cxt * 16 + cxl, cy = cyt * 4 + cyl, n = pair * 2 + nl;
                 const bool valid = (cx < p.Wc) && (n < p.B);
                 const size_t pix = ((size_t)n * p.H0 + (4 * cy + py)) * p.W0 + (4 * cx + px);
                 const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((acc * F0_MT + ti) * 128);
+                // The accumulators arrive one tile row (pixel) per thread.  Storing them row-per-thread sends every 16-byte piece
+                // as its own half-empty 32-byte sector request (ncu: 104 M write requests for 1.64 GB, the L1->crossbar request
+                // path the busiest unit of the kernel).  Instead each 32-channel chunk goes through a padded shared-memory tile
+                // and is re-read as (row = lane/8, 4 channels = lane%8): one warp store then covers four full 128-byte lines, and
+                // the same registers feed the pooling sums / maxima.
+                const int n_w = pair * 2 + (lg >> 1), cy_w = cyt * 4 + ((lg & 1) << 1);     // image / first coarse row of this warp's 32 rows
+                const int rr4 = lane >> 3, q = lane & 7;
+                float* rt = red + (warp - 2) * (32 * F0_RS);
+                float* wr = wred + ti * (8 * 128);
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32(taddr + c0, r);
                     tc_wait_ld();
-                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = fmaxf(__uint_as_float(r[j]) + sbias[c0 + j], 0.f);      // folded BN shift + ReLU
-                    if (valid) {
-                        float4* o = reinterpret_cast<float4*>(p.out + pix * 128 + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    for (int j = 0; j < 8; j++) {
+                        float4 v;
+                        v.x = fmaxf(__uint_as_float(r[4 * j + 0]) + sbias[c0 + 4 * j + 0], 0.f);     // folded BN shift + ReLU
+                        v.y = fmaxf(__uint_as_float(r[4 * j + 1]) + sbias[c0 + 4 * j + 1], 0.f);
+                        v.z = fmaxf(__uint_as_float(r[4 * j + 2]) + sbias[c0 + 4 * j + 2], 0.f);
+                        v.w = fmaxf(__uint_as_float(r[4 * j + 3]) + sbias[c0 + 4 * j + 3], 0.f);
+                        *reinterpret_cast<float4*>(rt + lane * F0_RS + 4 * j) = v;
                     }
-                    // fused global avg/max pooling: per-warp transpose so that lane j reduces channel c0+j over the warp's 32 pixels
-                    // (masked rows add 0; every value is >= 0 after the ReLU, so 0 never wins a max that has a valid row)
-                    float* rt = red + lg * (32 * 33);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) rt[lane * 33 + j] = valid ? v[j] : 0.f;
                     __syncwarp();
-                    float sm_ = 0.f, mx_ = 0.f;
-                    for (int rr = 0; rr < 32; rr++) { const float x = rt[rr * 33 + lane]; sm_ += x; mx_ = fmaxf(mx_, x); }
-                    wred[(lg * 2 + 0) * 128 + c0 + lane] = sm_;
-                    wred[(lg * 2 + 1) * 128 + c0 + lane] = mx_;
+                    float4 sm4 = make_float4(0.f, 0.f, 0.f, 0.f), mx4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int rr = it * 4 + rr4;                                         // tile row within this warp's 32
+                        const int cx_r = cxt * 16 + (rr & 15), cy_r = cy_w + (rr >> 4);
+                        const float4 x = *reinterpret_cast<const float4*>(rt + rr * F0_RS + 4 * q);
+                        if (n_w < p.B && cx_r < p.Wc) {
+                            if (!(p.skip & 8)) {                                             // values are >= 0 after the ReLU
+                                sm4.x += x.x; sm4.y += x.y; sm4.z += x.z; sm4.w += x.w;
+                                mx4.x = fmaxf(mx4.x, x.x); mx4.y = fmaxf(mx4.y, x.y); mx4.z = fmaxf(mx4.z, x.z); mx4.w = fmaxf(mx4.w, x.w);
+                            }
+                            if (!(p.skip & 4))
+                                *reinterpret_cast<float4*>(p.out + (((size_t)n_w * p.H0 + (4 * cy_r + py)) * p.W0 + (4 * cx_r + px)) * 128 + c0 + 4 * q) = x;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 8; o <= 16; o <<= 1) {                                      // combine the 4 row groups (lanes q, q+8, q+16, q+24)
+                        sm4.x += __shfl_xor_sync(0xffffffffu, sm4.x, o); sm4.y += __shfl_xor_sync(0xffffffffu, sm4.y, o);
+                        sm4.z += __shfl_xor_sync(0xffffffffu, sm4.z, o); sm4.w += __shfl_xor_sync(0xffffffffu, sm4.w, o);
+                        mx4.x = fmaxf(mx4.x, __shfl_xor_sync(0xffffffffu, mx4.x, o)); mx4.y = fmaxf(mx4.y, __shfl_xor_sync(0xffffffffu, mx4.y, o));
+                        mx4.z = fmaxf(mx4.z, __shfl_xor_sync(0xffffffffu, mx4.z, o)); mx4.w = fmaxf(mx4.w, __shfl_xor_sync(0xffffffffu, mx4.w, o));
+                    }
+                    if (lane < 8) {
+                        *reinterpret_cast<float4*>(wr + (lg * 2 + 0) * 128 + c0 + 4 * q) = sm4;
+                        *reinterpret_cast<float4*>(wr + (lg * 2 + 1) * 128 + c0 + 4 * q) = mx4;
+                    }
                     __syncwarp();
                 }
-                // rows 0..63 belong to image pair*2, rows 64..127 to the next one: combine warps {0,1} and {2,3}
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int et = (warp - 2) * 32 + lane;                      // 0..127 -> channel
+                // rows 0..63 belong to image pair*2, rows 64..127 to the next one: combine lane groups {0,1} and {2,3} of this tile
+                // (named barrier 1 + ti over the tile's 4 warps)
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + ti) : "memory");
+                const int et = ((warp - 2) & 3) * 32 + lane;                // 0..127 -> channel
                 const int part = (cyt * p.tiles_cx + cxt) * 16 + sp;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int n = pair * 2 + h;
                     if (n < p.B) {
                         float* dst = p.pool_part + ((size_t)n * p.parts + part) * 256;
-                        // warp index in wred = TMEM lane group (warp & 3): lane groups 0,1 hold rows 0..63, groups 2,3 rows 64..127
-                        dst[et] = wred[((2 * h) * 2 + 0) * 128 + et] + wred[((2 * h + 1) * 2 + 0) * 128 + et];
-                        dst[128 + et] = fmaxf(wred[((2 * h) * 2 + 1) * 128 + et], wred[((2 * h + 1) * 2 + 1) * 128 + et]);
+                        dst[et] = wr[((2 * h) * 2 + 0) * 128 + et] + wr[((2 * h + 1) * 2 + 0) * 128 + et];
+                        dst[128 + et] = fmaxf(wr[((2 * h) * 2 + 1) * 128 + et], wr[((2 * h + 1) * 2 + 1) * 128 + et]);
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + ti) : "memory");
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -239,7 +281,7 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
 // pooling partials per image written by the kernel for an S x S input
 int fpn0_fused_parts(int S) { const int Hc = S / 8; return (Hc / 4) * ((Hc + 15) / 16) * 16; }
 
-// f0t: tf32-rounded stem output [B][S/2][S/2][16]; lat1: tf32-rounded lateral level 1 [B][S/8][S/8][128] (top-down sum included);
+// f0t: tf32-rounded stem output as 16 sub-position planes [qy*4+qx][NB][S/8][S/8][16] (NB = B rounded up to even); lat1: tf32-rounded lateral level 1 [B][S/8][S/8][128] (top-down sum included);
 // out: fpn0 [B][S/2][S/2][128] fp32; pool_part: [B][fpn0_fused_parts(S)][2][128].  Buffers must extend one image past an odd B.
 int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, float* out, float* pool_part, int B, int S, cudaStream_t s) {
     EncodeTiledFn enc = get_encode();
@@ -260,19 +302,22 @@ int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, float*
         m += ((py == 0 || py == 3) ? 2 : 1) * ((px == 0 || px == 3) ? 2 : 1);
     }
     p.bias = plan->fpn_conv[0].bias; p.out = out; p.pool_part = pool_part;
-    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * 128 + 4 * (4 * 32 * 33 + 8 * 128) + 64;
+    static const int skip_env = getenv("KPD_FPN0_SKIP") ? atoi(getenv("KPD_FPN0_SKIP")) : 0;
+    p.skip = skip_env;
+    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * 128 + 4 * (F0_EPI_WARPS * 32 * F0_RS + 2 * 8 * 128) + 64;
     int stages = (227 * 1024 - misc) / F0_STAGE; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("fpn0_fused: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
     p.stages = stages;
     const size_t smem = (size_t)stages * F0_STAGE + misc;
     const cuuint64_t NB = (cuuint64_t)(pairs * 2);            // image extent rounded up to the pair the boxes span
+    p.NB = pairs * 2;
 
     CUtensorMap tmF, tmL, tmW1, tmW2;
     {
-        cuuint64_t dims[4] = {16, (cuuint64_t)p.W0, (cuuint64_t)p.H0, NB};
-        cuuint64_t strides[3] = {64, (cuuint64_t)p.W0 * 64, (cuuint64_t)p.H0 * p.W0 * 64};
-        cuuint32_t box[4] = {16, 64, 16, 2};                  // traversal extents: every 4th pixel -> 16 x 4 pixels x 2 images
-        cuuint32_t es[4] = {1, 4, 4, 1};
+        cuuint64_t dims[4] = {16, (cuuint64_t)p.Wc, (cuuint64_t)p.Hc, 16 * NB};       // [plane][image] folded into the outer dimension
+        cuuint64_t strides[3] = {64, (cuuint64_t)p.Wc * 64, (cuuint64_t)p.Hc * p.Wc * 64};
+        cuuint32_t box[4] = {16, 16, 4, 2};
+        cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(f0t), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("fpn0_fused: cuTensorMapEncodeTiled(f0) failed: %d", (int)r); return KPD_ERR_STATE; }
