@@ -80,8 +80,11 @@ constexpr int UMMA_THREADS = 192;
 // MT = M-tiles (128 pixels each) sharing one weight stage, RB = bytes of K per shared-memory row (128, or 64 for the
 // 16-channel fp32 lateral); both compile-time so that the single MMA-issuing thread runs a fully unrolled, lean loop
 // (its per-instruction overhead directly limits tensor throughput).
-template <bool BF16, int MT, int RB>
-__global__ void __launch_bounds__(UMMA_THREADS, 1)
+// EW = epilogue warps: 4 (one per TMEM lane group) or 8 (two per lane group, each draining half of the output channels --
+// the epilogue of a tile is a dependent chain of tcgen05.ld -> bias/ReLU -> convert -> stores per 32-channel chunk, and with
+// K as short as 576 (head conv 64->256) one warp per lane group cannot drain a tile in the time the MMAs need for the next).
+template <bool BF16, int MT, int RB, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x (A | B)] | barriers | tmem slot | bias
@@ -110,7 +113,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
@@ -190,6 +193,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {                                            // ---------------- epilogue warps 2..5
         const int lg = warp & 3;                        // TMEM lane group this warp may access
+        const int chalf = (warp - 2) >> 2;              // EW == 8: which half of the output channels
+        const int cbeg = EW == 8 ? chalf * (p.Cout >> 1) : 0, cend = EW == 8 ? cbeg + (p.Cout >> 1) : p.Cout;
         const int row = lg * 32 + lane;
         const int rw = row % p.tw, rh = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
         int acc = 0; uint32_t acc_phase = 0;
@@ -204,7 +209,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool valid = (w < p.W) && (h < p.H) && (n < n_live);
             const size_t pix = ((size_t)n * p.H + h) * p.W + w;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((acc * MT + ti) * p.Cout);
-            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+            for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 uint32_t r[32];
                 tc_ld32(taddr + c0, r);
                 tc_wait_ld();
@@ -479,9 +484,19 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     const int grid = std::min((total_tiles + mt - 1) / mt, plan->sm_count);
 #define KPD_LAUNCH_UMMA(BF, MTV, RBV)                                                                                     \
     do {                                                                                                                  \
-        KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BF, MTV, RBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv_umma_kernel<BF, MTV, RBV><<<grid, UMMA_THREADS, smem, s>>>(tmA, tmB, p);                                     \
+        if (ew8) {                                                                                                        \
+            KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BF, MTV, RBV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            conv_umma_kernel<BF, MTV, RBV, 8><<<grid, 64 + 32 * 8, smem, s>>>(tmA, tmB, p);                               \
+        } else {                                                                                                          \
+            KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BF, MTV, RBV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            conv_umma_kernel<BF, MTV, RBV, 4><<<grid, 64 + 32 * 4, smem, s>>>(tmA, tmB, p);                               \
+        }                                                                                                                 \
     } while (0)
+    // KPD_CONV_EW8=1: two epilogue warps per TMEM lane group (not with fused pooling, whose per-warp reductions assume 4 warps).
+    // Measured neutral on the head convs (0.277 vs 0.266 ms for 64->256): their short-K tiles are bound by operand and
+    // output traffic, not by the epilogue's dependent chain, so the default stays at 4.
+    static const bool ew_env8 = getenv("KPD_CONV_EW8") != nullptr;
+    const bool ew8 = ew_env8 && !pool_part && (c.cout % 64 == 0);
     if (row_bytes == 64) {
         if (prec_bf16 || mt != 1) { set_error("conv_dense_umma: 64-byte K rows are built for tf32, mt=1"); return KPD_ERR_UNSUPPORTED; }
         KPD_LAUNCH_UMMA(false, 1, 64);
