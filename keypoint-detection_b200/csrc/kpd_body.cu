@@ -313,7 +313,7 @@ static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool,
 // selects the 3xTF32 mma.sync predecessor), every depthwise conv one batch-wide TMA-staged kernel (kpd_dw.cu).  At the batch sizes of the benchmark configs the per-image problems (<= 56x56 pixels)
 // are too small to fill an SM, so the batch-wide form beats the one-cluster-per-image fused kernel (kpd_mbconv.cu);
 // the intermediates (expanded / depthwise tensors) stay L2-resident for B*H*W*C*4 B <= ~100 MB.
-static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
     float* f0_tf32 = want_f0_tf32 ? reinterpret_cast<float*>(scratch + sm.f0_tf32) : nullptr;
@@ -338,7 +338,7 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
         const int Ho = H / m.stride;
         const float* x = cur;
         if (m.w_exp) {
-            PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act;
+            PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.Wu = m.wu_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act; a.exact = strict_fp32;
             ProfScope ps("body.pointwise", s);
             KPD_TRY(pointwise_mma(a, p->sm_count, s));
             x = expand;
@@ -350,12 +350,12 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
             KPD_TRY(launch_se_fc(m, se_pool, pool_parts, se_scale, B, 1.f / (float)(Ho * Ho), s));
         }
         float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
-        PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.Wraw = m.w_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE;
+        PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.Wraw = m.w_proj; a.Wu = m.wu_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE; a.exact = strict_fp32;
         a.se_scale = m.se ? se_scale : nullptr; a.hw = Ho * Ho; a.res = m.res ? cur : nullptr; a.res_mode = m.res ? 1 : 0;
         { ProfScope ps("body.pointwise", s); KPD_TRY(pointwise_mma(a, p->sm_count, s)); }
         cur = dst; H = Ho;
     }
-    PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.Wraw = p->w_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH;
+    PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.Wraw = p->w_last; a.Wu = p->wu_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH; a.exact = strict_fp32;
     ProfScope ps("body.pointwise", s);
     return pointwise_mma(a, p->sm_count, s);
 }
@@ -363,7 +363,7 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
 int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     static const bool fused = getenv("KPD_BODY_FUSED") != nullptr;           // one-cluster-per-image fused MBConv kernels
     // default in every precision mode: the batch-wide pipeline is exact fp32 on CUDA cores (FFMA GEMMs, FMA depthwise)
-    if (!fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, want_f0_tf32, ws, L, s); }
+    if (!fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, strict_fp32, want_f0_tf32, ws, L, s); }
     ProfScope ps("body", s);
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
@@ -555,8 +555,8 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
     if ((int64_t)B * hs[0] * hs[0] >= (int64_t)1 << 31) { set_error("fpn laterals: B*H*W = %lld pixels exceeds the 32-bit pixel index", (long long)B * hs[0] * hs[0]); return KPD_ERR_UNSUPPORTED; }
     (void)strict_fp32;                                  // every lateral is exact fp32 on CUDA cores; the modes differ only in round_tf32
     for (int i = 3; i >= 1; i--) {                       // laterals 3..1: fp32 GEMM + nearest-upsample add in the epilogue
-        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.Wraw = p->w_lat[i]; a.out = lat[i];
-        a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i];
+        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.Wraw = p->w_lat[i]; a.Wu = p->wu_lat[i]; a.out = lat[i];
+        a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i]; a.exact = strict_fp32;
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
         a.round_tf32 = (composed && i == 1) ? 1 : 0;
         KPD_TRY(pointwise_mma(a, p->sm_count, s));

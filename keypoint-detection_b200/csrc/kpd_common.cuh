@@ -70,6 +70,7 @@ struct MBBlock {
     int cin, k, exp, cout, se, act, stride, res, sq;
     // device pointers (fp32). pointwise weights are [Cin][Cout] (K-major rows, cout contiguous)
     const float *w_exp, *b_exp;     // expand 1x1 (+folded BN)        [cin][exp], [exp]   (null if exp==cin)
+    const float *wu_exp, *wu_proj;  // the same 1x1 weights as tf32 hi / lo split [2][Np][Kp] for the tcgen05 GEMM (kpd_pwu.cu)
     const float *w_dw, *b_dw;       // depthwise kxk (+folded BN)     [k*k][exp], [exp]
     const float *w_fc1, *b_fc1;     // SE fc1                          [exp][sq], [sq]
     const float *w_fc2, *b_fc2;     // SE fc2                          [sq][exp], [exp]
@@ -99,6 +100,7 @@ struct kpd_plan {
     const float *w_stem, *b_stem;                 // [3*3*cin][16], [16]
     kpd::MBBlock blocks[11];
     const float *w_last, *b_last;                 // f12 [96][576], [576]
+    const float* wu_last; const float* wu_lat[4];  // tf32 hi / lo splits for the tcgen05 pointwise GEMM
     const float4* wf_last;                        // f12 as 3xTF32 mma fragments
     // fpn
     const float* w_lat[4];                        // [cin_i][128]
@@ -150,7 +152,11 @@ struct PwMma {
     int H, W, up;                            // res_mode 2: output map H x W, coarse map (H/up) x (W/up), N channels
     int round_tf32;                          // round the result to tf32 (it feeds a kind::tf32 tcgen05 MMA)
     const float* Wraw;                       // [K][N] row-major fp32 (CUDA-core FFMA GEMM, kpd_pwf.cu)
+    const float* Wu;                         // [2][Np][Kp] tf32 hi / lo split, K-major rows (tcgen05 3xTF32 GEMM, kpd_pwu.cu)
+    int exact;                               // 1: strict-fp32 mode -- CUDA-core FFMA GEMM only
 };
+int pointwise_umma(const PwMma& p, int sm_count, cudaStream_t s);
+void pwu_chunks(int N, int* nchunks, int* Nc);
 int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s);
 int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s);
 

@@ -142,6 +142,23 @@ static size_t pack_mma_frag(Blob& B, size_t off_w, int K, int N) {
     return off;
 }
 
+// tf32 hi / lo split of a [K][N] matrix stored in the blob at `off_w`, as K-major rows [2][Np][Kp] (kpd_pwu.cu)
+static size_t pack_umma_split(Blob& B, size_t off_w, int K, int N) {
+    int nchunks, Nc; kpd::pwu_chunks(N, &nchunks, &Nc);
+    const int Np = nchunks * Nc, Kp = (K + 31) & ~31;
+    const size_t off = B.alloc(sizeof(float) * 2 * (size_t)Np * Kp);
+    float* d = B.f(off);
+    memset(d, 0, sizeof(float) * 2 * (size_t)Np * Kp);
+    for (int n = 0; n < N; n++)
+        for (int k = 0; k < K; k++) {
+            const float w = B.f(off_w)[(size_t)k * N + n];
+            const float hi = to_tf32(w);
+            d[(size_t)n * Kp + k] = hi;
+            d[((size_t)Np + n) * Kp + k] = to_tf32(w - hi);
+        }
+    return off;
+}
+
 static size_t pack_raw(Blob& B, const float* src, size_t n) {
     size_t off = B.alloc(sizeof(float) * n);
     memcpy(B.f(off), src, sizeof(float) * n);
@@ -223,6 +240,7 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.exp, m.cin, 1, ow, ob);
             reg(&m.w_exp, ow); reg(&m.b_exp, ob);
             reg(&m.wf_exp, pack_mma_frag(B, ow, m.cin, m.exp));
+            reg(&m.wu_exp, pack_umma_split(B, ow, m.cin, m.exp));
         }
         {   // depthwise [exp][1][k][k] -> [k*k][exp]
             const float* w = c.next(); BN bn = read_bn(c);
@@ -244,6 +262,7 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.cout, m.exp, 1, ow, ob);
             reg(&m.w_proj, ow); reg(&m.b_proj, ob);
             reg(&m.wf_proj, pack_mma_frag(B, ow, m.exp, m.cout));
+            reg(&m.wu_proj, pack_umma_split(B, ow, m.exp, m.cout));
         }
     }
     {   // features.12
@@ -251,6 +270,7 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, 576, 96, 1, ow, ob);
         reg(&p->w_last, ow); reg(&p->b_last, ob);
         reg(&p->wf_last, pack_mma_frag(B, ow, 96, 576));
+        reg(&p->wu_last, pack_umma_split(B, ow, 96, 576));
     }
     const int fpn_in[4] = {16, 24, 48, 576};
     const float* w_lat0_raw = nullptr;
@@ -260,6 +280,7 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         pack_conv_kc(B, w, nullptr, nullptr, 0, 128, fpn_in[i], 1, ow, ob);
         reg(&p->w_lat[i], ow);
         reg(&p->wf_lat[i], pack_mma_frag(B, ow, fpn_in[i], 128));
+        reg(&p->wu_lat[i], pack_umma_split(B, ow, fpn_in[i], 128));
     }
     auto dense = [&](DenseConv& d, const float* w, const float* cb, const BN* bn, double eps, int cout, int cin, int k) {
         size_t off[4]; pack_dense(B, w, cb, bn, eps, cout, cin, k, off);

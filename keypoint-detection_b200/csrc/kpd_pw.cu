@@ -141,7 +141,17 @@ __global__ void __launch_bounds__(PW_THREADS) pw_mma_kernel(const PwMma p, int t
 }
 
 int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s) {
-    static const bool use_mma = getenv("KPD_PW_MMA") != nullptr;     // 3xTF32 mma.sync predecessor, kept for A/B timing
+    // Dispatch between the three GEMM implementations.  Default (non-strict modes): tcgen05 3xTF32 (kpd_pwu.cu), except for the
+    // shapes where its per-tile pipeline (TMA -> split -> MMA -> epilogue) measured slower than the CUDA-core kernel: K <= 16
+    // (one half-empty slab per tile), very narrow outputs with a residual, and the K = 24 lateral with the upsampled residual.
+    // Strict fp32 always takes the exact FFMA kernel.  KPD_PW_FFMA=1 / KPD_PW_UMMA=1 / KPD_PW_MMA=1 force one implementation.
+    static const bool use_mma = getenv("KPD_PW_MMA") != nullptr;       // 3xTF32 mma.sync predecessor, kept for A/B timing
+    static const bool force_umma = getenv("KPD_PW_UMMA") != nullptr;
+    static const bool force_ffma = getenv("KPD_PW_FFMA") != nullptr;
+    if (!use_mma && p.Wu && !p.exact && !force_ffma) {
+        const bool prefer_ffma = (p.K <= 16) || (p.N <= 24 && p.res) || (p.res && p.res_mode == 2 && p.K <= 24);
+        if (force_umma || !prefer_ffma) return pointwise_umma(p, sm_count, s);
+    }
     if (!use_mma && p.Wraw) return pointwise_ffma(p, sm_count, s);
     if ((p.K & 7) || (p.N & 7)) { set_error("pointwise_mma: K and N must be multiples of 8 (got %d, %d)", p.K, p.N); return KPD_ERR_UNSUPPORTED; }
     if (p.M <= 0) return 0;
