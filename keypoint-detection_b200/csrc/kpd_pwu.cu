@@ -6,7 +6,7 @@
 // channel top-k is decided by score gaps of 1e-6..1e-5), which one tf32 MMA does not give; three do:
 //     A W  ~=  A_hi W_hi + A_lo W_hi + A_hi W_lo,   x_hi = tf32(x),  x_lo = tf32(x - x_hi)       (error ~2^-21 relative)
 // W_hi / W_lo are split on the host.  A is split ON CHIP: a 128-row x 32-float slab lands in shared memory by TMA (128-byte
-// swizzle), four "split" warps rewrite it element-wise into an A_hi and an A_lo slab at the same swizzled offsets (multiplying
+// swizzle), four "split" warps rewrite it element-wise (A_hi in place, A_lo into a second slab at the same swizzled offsets (multiplying
 // by the SE excitation on the way -- the swizzle is undone only to find each 16-byte chunk's k index), fence.proxy.async, and
 // the MMA thread issues 3 x 4 tcgen05.mma (kind::tf32) per slab into a TMEM accumulator.  Even at three passes the tensor
 // core has 5x the MAC rate of the 128 FFMA lanes, so these GEMMs become streams of their activations.
@@ -40,7 +40,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int S = p.stages;
-    // stage: [raw A | A_hi | A_lo | B_hi (Nc rows x 128 B) | B_lo]
+    // stage: [A (raw fp32 from TMA, rewritten in place as A_hi) | A_lo | B_hi (Nc rows x 128 B) | B_lo]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
     // bars: [0,S) full (TMA landed), [S,2S) split done, [2S,3S) free (MMAs retired), [3S,3S+2) tmem full, [3S+2,3S+4) tmem empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
@@ -85,8 +85,8 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_expect_tx(full_bar(stage), (uint32_t)PU_A + 2u * b_bytes);
                     const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                     tma_load_2d(sa, &tmA, full_bar(stage), sl * 32, tm * 128);
-                    tma_load_2d(sa + 3 * PU_A, &tmB, full_bar(stage), sl * 32, n0);
-                    tma_load_2d(sa + 3 * PU_A + b_bytes, &tmB, full_bar(stage), sl * 32, p.Np + n0);
+                    tma_load_2d(sa + 2 * PU_A, &tmB, full_bar(stage), sl * 32, n0);
+                    tma_load_2d(sa + 2 * PU_A + b_bytes, &tmB, full_bar(stage), sl * 32, p.Np + n0);
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
@@ -103,8 +103,8 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(split_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-                    const uint64_t a_hi = make_sdesc_rb(sa + PU_A, 128), a_lo = make_sdesc_rb(sa + 2 * PU_A, 128);
-                    const uint64_t b_hi = make_sdesc_rb(sa + 3 * PU_A, 128), b_lo = make_sdesc_rb(sa + 3 * PU_A + b_bytes, 128);
+                    const uint64_t a_hi = make_sdesc_rb(sa, 128), a_lo = make_sdesc_rb(sa + PU_A, 128);
+                    const uint64_t b_hi = make_sdesc_rb(sa + 2 * PU_A, 128), b_lo = make_sdesc_rb(sa + 2 * PU_A + b_bytes, 128);
                     const int ksteps = min(4, (p.K - sl * 32 + 7) >> 3);        // 8 floats of K per MMA
                     for (int k4 = 0; k4 < ksteps; k4++) {                        // small terms first
                         tc_mma<false>(d_tmem, a_lo + 2 * k4, b_hi + 2 * k4, idesc, (sl | k4) != 0 ? 1u : 0u);
@@ -130,22 +130,27 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 8; i++) img[i] = min(m0 + (uint32_t)((t >> 3) + 16 * i), p.M - 1) / (uint32_t)p.hw;
             }
             for (int sl = 0; sl < nslabs; sl++) {
+                // SE excitation factors of this slab's chunks: loaded before the wait, so their L2 latency hides behind the TMA's
+                float4 sc[8];
+                if (p.se_scale) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int f = t + 128 * i, row = f >> 3, k = sl * 32 + (((f & 7) ^ (row & 7)) << 2);
+                        sc[i] = k < p.K ? __ldg(reinterpret_cast<const float4*>(p.se_scale + (size_t)img[i] * p.K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
                 mbar_wait(full_bar(stage), phase);
                 uint8_t* sp = smem + (size_t)stage * p.stage_bytes;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    const int f = t + 128 * i, row = f >> 3, kchunk = (f & 7) ^ (row & 7);        // undo the 128-byte swizzle for k only
+                    const int f = t + 128 * i;                                   // float4 index: row f >> 3, stored chunk position f & 7
                     float4 a = *reinterpret_cast<const float4*>(sp + f * 16);
-                    const int k = sl * 32 + kchunk * 4;
-                    if (p.se_scale && k < p.K) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.se_scale + (size_t)img[i] * p.K + k));
-                        a.x *= sc.x; a.y *= sc.y; a.z *= sc.z; a.w *= sc.w;
-                    }
+                    if (p.se_scale) { a.x *= sc[i].x; a.y *= sc[i].y; a.z *= sc[i].z; a.w *= sc[i].w; }
                     float4 hi, lo;
                     hi.x = tf32_rna(a.x); hi.y = tf32_rna(a.y); hi.z = tf32_rna(a.z); hi.w = tf32_rna(a.w);
                     lo.x = tf32_rna(a.x - hi.x); lo.y = tf32_rna(a.y - hi.y); lo.z = tf32_rna(a.z - hi.z); lo.w = tf32_rna(a.w - hi.w);
-                    *reinterpret_cast<float4*>(sp + PU_A + f * 16) = hi;
-                    *reinterpret_cast<float4*>(sp + 2 * PU_A + f * 16) = lo;
+                    *reinterpret_cast<float4*>(sp + f * 16) = hi;                  // in place: same thread, same 16 bytes
+                    *reinterpret_cast<float4*>(sp + PU_A + f * 16) = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
@@ -255,10 +260,10 @@ int pointwise_umma(const PwMma& a, int sm_count, cudaStream_t s) {
     if (total >= ((int64_t)1 << 31)) { set_error("pointwise_umma: too many tiles"); return KPD_ERR_UNSUPPORTED; }
     p.total = (int)total;
     p.act = a.act; p.hw = a.hw > 0 ? a.hw : 1; p.res_mode = a.res ? a.res_mode : 0; p.H = a.H; p.W = a.W; p.up = a.up > 0 ? a.up : 1; p.round_tf32 = a.round_tf32;
-    p.stage_bytes = 3 * PU_A + 2 * p.Nc * 128;
+    p.stage_bytes = 2 * PU_A + 2 * p.Nc * 128;
     const int misc = 1024 /*align*/ + 8 * (3 * 8 + 4) + 32 + 4 * PU_MAXN + 4 * (PU_EPI_WARPS * 32 * PU_RS) + 64;
     if (p.Np > PU_MAXN) { set_error("pointwise_umma: N = %d too wide", a.N); return KPD_ERR_UNSUPPORTED; }
-    int stages = (227 * 1024 - misc) / p.stage_bytes; if (stages > 4) stages = 4;
+    int stages = (227 * 1024 - misc) / p.stage_bytes; if (stages > 6) stages = 6;
     if (stages < 2) { set_error("pointwise_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
     p.stages = stages;
     const size_t smem = (size_t)stages * p.stage_bytes + misc;
