@@ -116,7 +116,7 @@ def trunk_rooflines(kern, B, S, pk, clocks):
         out["depthwise (11 TMA-staged kernels; layer in+out bytes)"] = {
             "achieved_gbs": B * dw_bytes / (kern["body.depthwise"] * 1e-3) / 1e9, "peak_gbs": pk["hbm"]}
     if "body.pointwise" in kern:
-        out["pointwise GEMMs (22 CUDA-core fp32 kernels)"] = {
+        out["pointwise GEMMs (22 kernels: tcgen05 3xTF32, CUDA-core fp32 for K<=16 / narrow residual shapes; useful flops)"] = {
             "achieved_tflops": B * pw_flops / (kern["body.pointwise"] * 1e-3) / 1e12, "peak_tflops": fp32_peak,
             "peak_source": f"nominal fp32 FMA: 148 SM x 128 lanes x 2 x {sm_mhz:.0f} MHz"}
     if "fpn_laterals.lat0" in kern:
