@@ -448,3 +448,54 @@ ScratchMap scratch_map(int B, int S, int n_rois) {
     return m;
 }
 }  // namespace kpd
+
+// ------------------------------------------------------------------------------------------------ tensor-map cache
+#include "kpd_tma.cuh"
+#include <unordered_map>
+#include <mutex>
+namespace kpd {
+EncodeTiledFn kpd_driver_encode() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            return reinterpret_cast<EncodeTiledFn>(ptr);
+        return (EncodeTiledFn) nullptr;
+    }();
+    return fn;
+}
+namespace {
+struct TmKey {
+    uint64_t w[20];
+    bool operator==(const TmKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmHash {
+    size_t operator()(const TmKey& k) const { uint64_t h = 1469598103934665603ull; for (uint64_t v : k.w) { h ^= v; h *= 1099511628211ull; } return (size_t)h; }
+};
+std::mutex g_tm_mu;
+std::unordered_map<TmKey, CUtensorMap, TmHash> g_tm_cache;
+}  // namespace
+CUresult kpd_encode_tiled(CUtensorMap* tm, CUtensorMapDataType dtype, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+                          const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* es, CUtensorMapInterleave il,
+                          CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+    EncodeTiledFn drv = kpd_driver_encode();
+    if (!drv || rank > 5) return CUDA_ERROR_NOT_SUPPORTED;
+    int dev = 0; cudaGetDevice(&dev);
+    TmKey k; memset(&k, 0, sizeof(k));
+    k.w[0] = (uint64_t)(uintptr_t)ptr;
+    k.w[1] = (uint64_t)dtype | ((uint64_t)rank << 8) | ((uint64_t)il << 16) | ((uint64_t)sw << 24) | ((uint64_t)l2 << 32) | ((uint64_t)oob << 40) | ((uint64_t)dev << 48);
+    for (cuuint32_t i = 0; i < rank; i++) { k.w[2 + i] = dims[i]; k.w[12 + i] = ((uint64_t)box[i] << 32) | es[i]; }
+    for (cuuint32_t i = 0; i + 1 < rank; i++) k.w[7 + i] = strides[i];
+    {
+        std::lock_guard<std::mutex> lock(g_tm_mu);
+        auto it = g_tm_cache.find(k);
+        if (it != g_tm_cache.end()) { *tm = it->second; return CUDA_SUCCESS; }
+    }
+    const CUresult r = drv(tm, dtype, rank, ptr, dims, strides, box, es, il, sw, l2, oob);
+    if (r == CUDA_SUCCESS) {
+        std::lock_guard<std::mutex> lock(g_tm_mu);
+        if (g_tm_cache.size() > 8192) g_tm_cache.clear();
+        g_tm_cache.emplace(k, *tm);
+    }
+    return r;
+}
+}  // namespace kpd

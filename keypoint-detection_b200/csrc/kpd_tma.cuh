@@ -104,14 +104,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static inline EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr; cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
+// cuTensorMapEncodeTiled behind a process-wide cache (kpd_plan.cu): a forward encodes ~70 descriptors whose arguments --
+// workspace pointers included -- repeat from call to call; each driver encode costs several microseconds of host time.
+CUresult kpd_encode_tiled(CUtensorMap* tm, CUtensorMapDataType dtype, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
+                          const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* es, CUtensorMapInterleave il,
+                          CUtensorMapSwizzle sw, CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob);
+EncodeTiledFn kpd_driver_encode();            // the raw driver entry point (null if unavailable)
+
+static inline EncodeTiledFn get_encode() { return kpd_driver_encode() ? &kpd_encode_tiled : nullptr; }
 
 }  // namespace kpd

@@ -5,6 +5,7 @@ reference's MultiPersonKeypointModel (keypoint_model.py:46-210); the whole forwa
 hand-written sm_100a kernels behind the C-ABI of libkpd_b200.so (one call per forward, no per-box Python loop,
 no host synchronisation).  Training (loss, backward) is outside the hot path and not provided.
 """
+import os
 from typing import Tuple
 
 import torch
@@ -53,6 +54,7 @@ class MultiPersonKeypointModel(nn.Module):
         self.set_precision(precision)
         self._plans = PlanCache(config.backbone.in_channels, config.num_keypoints)
         self._workspace = Workspace()
+        self._chunk_streams, self._chunk_workspaces = [], []     # host-input pipelining (forward)
         self._tensors = None
         self._last = None
 
@@ -120,7 +122,7 @@ class MultiPersonKeypointModel(nn.Module):
             raise NotImplementedError("forward() needs batch['bboxes']: the person-detector path has no reference semantics")
         if boxes.size(-1) != 4:
             raise ValueError(f"Invalid bboxes format: {boxes.shape}")
-        person_bboxes = [boxes[i] for i in range(boxes.size(0))]
+        person_bboxes = list(boxes.unbind(0))          # per-image box tensors, as the reference returns them (one op, not B slices)
         K = self.num_keypoints
         if boxes.size(0) == 0 or boxes.size(1) == 0:
             # keypoint_model.py:121-135 -- eval-mode empty result (note the reference's differing ranks)
@@ -132,28 +134,60 @@ class MultiPersonKeypointModel(nn.Module):
             raise ValueError(f"bboxes batch {boxes.size(0)} != image batch {batch_size}")
 
         with torch.cuda.device(dev):
-            x = as_cuda_f32(x, dev)
-            bx = as_cuda_f32(boxes, dev)
-            P, S = bx.size(1), x.size(2)
+            P, S = boxes.size(1), x.size(2)
             prec = N.PRECISIONS[self.precision]
-            L = plan.layout(batch_size, S, batch_size * P, prec)
-            ws = self._workspace.get(L.total_bytes, dev)
             heat = torch.empty(batch_size, P, K, 56, 56, device=dev, dtype=torch.float32)
             kpts = torch.empty(batch_size, P, 1, K, 2, device=dev, dtype=torch.float32)
             vis = torch.empty(batch_size, P, 1, K, 3, device=dev, dtype=torch.float32)
             tk = None
             if topk_override is not None:
                 tk = topk_override.to(device=dev, dtype=torch.int32).contiguous()
-            N.check(N.load().kpd_forward(plan.handle, prec, N.ptr(x), batch_size, S, N.ptr(bx), P, N.ptr(tk),
-                                         N.ptr(heat), N.ptr(kpts), N.ptr(vis), N.ptr(ws), L.total_bytes,
-                                         N.stream_ptr(dev)), "kpd_forward")
-            self._last = (ws, L, batch_size, S, batch_size * P, prec)
+            # Host-resident input (the DataLoader path): images are independent, so the batch is cut into a few chunks, each
+            # copied and processed on its own stream and workspace -- the H2D copy of chunk i+1 overlaps the kernels of chunk i.
+            # (Results are bit-identical to the one-shot path: nothing in the forward depends on an image's batch-mates.)
+            nchunks = 1
+            if x.device.type == "cpu" and tk is None:
+                want = int(os.environ.get("KPD_H2D_CHUNKS", "0")) or (2 if batch_size >= 128 else 1)
+                nchunks = max(1, min(want, batch_size // 32))
+            if nchunks == 1:
+                xd = as_cuda_f32(x, dev)
+                bx = as_cuda_f32(boxes, dev)
+                L = plan.layout(batch_size, S, batch_size * P, prec)
+                ws = self._workspace.get(L.total_bytes, dev)
+                N.check(N.load().kpd_forward(plan.handle, prec, N.ptr(xd), batch_size, S, N.ptr(bx), P, N.ptr(tk),
+                                             N.ptr(heat), N.ptr(kpts), N.ptr(vis), N.ptr(ws), L.total_bytes,
+                                             N.stream_ptr(dev)), "kpd_forward")
+                self._last = (ws, L, batch_size, S, batch_size * P, prec)
+            else:
+                cur = torch.cuda.current_stream(dev)
+                while len(self._chunk_streams) < nchunks:
+                    self._chunk_streams.append(torch.cuda.Stream(device=dev))
+                    self._chunk_workspaces.append(Workspace())
+                step = (batch_size + nchunks - 1) // nchunks
+                for i in range(nchunks):
+                    a, b = i * step, min(batch_size, (i + 1) * step)
+                    if a >= b:
+                        break
+                    st = self._chunk_streams[i]
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        xi = as_cuda_f32(x[a:b], dev)
+                        bi = as_cuda_f32(boxes[a:b], dev)
+                        L = plan.layout(b - a, S, (b - a) * P, prec)
+                        ws = self._chunk_workspaces[i].get(L.total_bytes, dev)
+                        N.check(N.load().kpd_forward(plan.handle, prec, N.ptr(xi), b - a, S, N.ptr(bi), P, None,
+                                                     N.ptr(heat[a:b]), N.ptr(kpts[a:b]), N.ptr(vis[a:b]), N.ptr(ws), L.total_bytes,
+                                                     N.stream_ptr(dev)), "kpd_forward")
+                        self._last = (ws, L, b - a, S, (b - a) * P, prec)     # stage views of the last chunk only
+                for i in range(nchunks):
+                    cur.wait_stream(self._chunk_streams[i])
         return {'heatmap': heat, 'keypoints': kpts, 'visibilities': vis, 'boxes': person_bboxes}
 
     @torch.no_grad()
     def predict(self, batch, **kw):
         """eval() + no_grad forward (BASELINE north star: the reference itself has no predict method)."""
-        self.eval()
+        if self.training:          # (Module.eval() walks the whole module tree: only when needed)
+            self.eval()
         return self.forward(batch, **kw)
 
     def stage_tensors(self):
