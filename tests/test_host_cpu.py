@@ -136,3 +136,41 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), os.path.join(base, f)
+
+
+def test_fpn0_composed_form_is_the_same_function():
+    """The algebra behind kpd_fpn0.cu, checked in fp64 on the CPU: conv3x3(L0 f0 + up4(lat1)) with zero padding equals
+    (A) a 3x3 conv of f0 with weights composed through L0 plus (B) for every sub-position (py,px) of a 4x4 block the
+    <= 4 coarse neighbours of lat1 times the sums of the taps that land in them -- 36 matrices in total, enumerated in
+    the order kpd_plan.cu packs them ((py, px, ny, nx) nested)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    B, H0, Hc, C = 2, 16, 4, 128
+    f0 = torch.randn(B, 16, H0, H0, dtype=torch.float64, generator=g)
+    lat1 = torch.randn(B, C, Hc, Hc, dtype=torch.float64, generator=g)
+    W0 = torch.randn(C, 16, dtype=torch.float64, generator=g)
+    Wc = torch.randn(C, C, 3, 3, dtype=torch.float64, generator=g)
+    lateral0 = torch.einsum("oc,bchw->bohw", W0, f0) + F.interpolate(lat1, scale_factor=4, mode="nearest")
+    want = F.conv2d(lateral0, Wc, padding=1)
+
+    def nbr(p, d):
+        q = p + d
+        return -1 if q < 0 else (1 if q > 3 else 0)
+
+    got = F.conv2d(f0, torch.einsum("octs,ci->oits", Wc, W0), padding=1)           # (A): K = 9 x 16
+    lat1p = F.pad(lat1, (1, 1, 1, 1))                                              # out-of-map coarse neighbours read zeros
+    n_mats = 0
+    for py in range(4):
+        for px in range(4):
+            for ny in (-1, 0, 1):
+                for nx in (-1, 0, 1):
+                    taps = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if nbr(py, dy) == ny and nbr(px, dx) == nx]
+                    if not taps:
+                        continue
+                    n_mats += 1
+                    A = sum(Wc[:, :, dy + 1, dx + 1] for dy, dx in taps)
+                    src = lat1p[:, :, 1 + ny:1 + ny + Hc, 1 + nx:1 + nx + Hc]
+                    got[:, :, py::4, px::4] += torch.einsum("oc,bchw->bohw", A, src)
+    assert n_mats == 36
+    assert float((got - want).abs().max()) < 1e-10
