@@ -172,8 +172,11 @@ def run_reference_arm(args, rank, world):
     line = {"metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": cb["ms_per_pass"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"reference CPU forward+decode, bounded sample: B=8 per step of the B={args.batch} config "
-                                   f"(1x{args.size}x{args.size}, P={args.persons})", "images_per_step": 8},
+            "config": {"workload": f"C2: B={args.batch} per GPU, 1x{args.size}x{args.size} images, P={args.persons} box/image, forward+decode, "
+                                   f"random-init weights (seed 0)",
+                       "global_batch": args.batch * world, "parallelism": f"dp{world} replicas", "precision": "fp32 (CPU)",
+                       "sample": f"bounded sample of that workload: each step is B=8 images (1x{args.size}x{args.size}, P={args.persons}) "
+                                 f"through the CPU port of the reference on all host cores; rank 0 only", "images_per_step": 8},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -293,7 +296,7 @@ def main():
                 "flops_per_launch": conv2_flops, "ms_per_launch": kern[dom]}
     line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 head / tf32 trunk, fp32 accumulate" if args.precision == "bf16" else ("tf32, fp32 accumulate" if args.precision == "fp32" else "fp32"),
+            "dtype": "bf16 head convs, tf32 FPN-0, 3xTF32 / fp32 trunk, fp32 accumulate" if args.precision == "bf16" else ("tf32 convs, 3xTF32 / fp32 trunk, fp32 accumulate" if args.precision == "fp32" else "fp32"),
             "data": "synthetic", "impl": "native",
             "config": {"workload": f"C2: B={B} per GPU, 1x{S}x{S} images, P={P} box/image, forward+decode, random-init weights (seed 0)",
                        "global_batch": B * world, "parallelism": f"dp{world} replicas", "precision": args.precision,
