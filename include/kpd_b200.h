@@ -117,9 +117,17 @@ int  kpd_fpn_levels123(const kpd_plan* plan, int batch, int size, void* d_worksp
 /* keypoint_model.py:27-44 MLP + sigmoid, :653-661 topk(64) sorted descending (ties: lower channel first) */
 int  kpd_channel_topk(const kpd_plan* plan, int batch, void* d_workspace, const kpd_workspace_layout* layout,
                       void* stream);
+/* keypoint_model.py:33-44 ChannelAttention.forward and :653-661 select_top_k_channels as a leaf op on a caller's tensor:
+ * d_feat_nchw fp32 [B,128,H,W] (hw = H*W) -> d_scores fp32 [B,128], d_topk int32 [B,64] (descending score, ties: lower
+ * channel first), d_selected fp32 NCHW [B,64,H,W] = the selected planes in rank order.  Any output may be NULL.
+ * d_scratch: B*512 floats. */
+int  kpd_channel_attention(const kpd_plan* plan, const float* d_feat_nchw, int batch, int hw, float* d_scores,
+                           int32_t* d_topk, float* d_selected, void* d_scratch, void* stream);
 /* keypoint_model.py:137-206: box compaction, roi_align (:212-228), HeatmapHead.forward
  * (heatmap_head.py:81-113), decode_heatmap (:250-313), convert_to_original_coords (:230-248), padding.
- * The workspace must have been laid out with max_rois >= batch*persons. */
+ * The workspace must have been laid out for this (batch, size, precision) with max_rois >= batch*persons: every stage
+ * entry point checks its arguments against `layout` and returns KPD_ERR_ARG on a mismatch.  Channel indices in
+ * d_topk_override are clamped to [0,128) on the device. */
 int  kpd_roi_head(const kpd_plan* plan, int precision, int batch, int size, const float* d_boxes, int persons,
                   const int32_t* d_topk_override, float* d_heatmap, float* d_keypoints, float* d_visibilities,
                   void* d_workspace, const kpd_workspace_layout* layout, void* stream);

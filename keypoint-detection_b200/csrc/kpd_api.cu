@@ -80,6 +80,16 @@ static int check_layout(const kpd_plan* plan, const void* ws, const kpd_workspac
     return 0;
 }
 
+// A stage call must use the (batch, size, ROI capacity, precision) its workspace layout was computed for: the offsets are
+// only valid for those, and a mismatch would let one stage tensor overrun the next.  n_rois / precision < 0 = not checked.
+static int check_stage(const kpd_workspace_layout& L, int B, int S, int n_rois, int precision, const char* who) {
+    KPD_CHECK_ARG(B == L.batch, "%s: batch %d != %d the workspace layout was built for", who, B, L.batch);
+    KPD_CHECK_ARG(S < 0 || S == L.size, "%s: size %d != %d the workspace layout was built for", who, S, L.size);
+    KPD_CHECK_ARG(n_rois < 0 || n_rois <= L.max_rois, "%s: %d ROIs exceed the %d the workspace layout was built for", who, n_rois, L.max_rois);
+    KPD_CHECK_ARG(precision < 0 || precision == L.precision, "%s: precision %d != %d the workspace layout was built for", who, precision, L.precision);
+    return 0;
+}
+
 // NCHW fp32 [n,64,56,56] -> NHWC roi_feat + channel-attention pool partials (HeatmapHead.forward standalone).
 __global__ void __launch_bounds__(256) nchw_to_roi_kernel(const float* __restrict__ x, float* __restrict__ roi_feat,
                                                           float* __restrict__ part, int32_t* __restrict__ roi_slot,
@@ -144,6 +154,7 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     KPD_CHECK_ARG((int64_t)B * (S / 2) * (S / 2) < ((int64_t)1 << 30), "kpd_backbone_fpn0: B*(S/2)^2 = %lld exceeds the 32-bit pixel index of the trunk kernels", (long long)B * (S / 2) * (S / 2));
     KPD_CHECK_ARG(precision >= 0 && precision <= 2, "unknown precision %d", precision);
     const kpd_workspace_layout& L = *layout;
+    KPD_TRY(check_stage(L, B, S, -1, precision, "kpd_backbone_fpn0"));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     // FPN level 0: composed tcgen05 form (kpd_fpn0.cu; lateral 0 never materialised) unless strict fp32 or KPD_FPN0_CLASSIC=1
@@ -183,6 +194,7 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
 extern "C" int kpd_channel_topk(const kpd_plan* plan, int B, void* d_workspace, const kpd_workspace_layout* layout, void* stream) {
     KPD_TRY(check_layout(plan, d_workspace, layout));
     KPD_CHECK_ARG(B > 0, "kpd_channel_topk: batch must be > 0");
+    KPD_TRY(check_stage(*layout, B, -1, -1, -1, "kpd_channel_topk"));
     char* ws = static_cast<char*>(d_workspace);
     return run_scores_topk(plan, B, reinterpret_cast<const float*>(ws + layout->pool_avg), reinterpret_cast<const float*>(ws + layout->pool_max),
                            reinterpret_cast<float*>(ws + layout->scores), reinterpret_cast<int32_t*>(ws + layout->topk),
@@ -200,6 +212,7 @@ extern "C" int kpd_roi_head(const kpd_plan* plan, int precision, int B, int S, c
     KPD_CHECK_ARG(precision >= 0 && precision <= 2, "unknown precision %d", precision);
     KPD_CHECK_ARG(layout->elt_bytes == (size_t)(precision == KPD_PREC_BF16 ? 2 : 4), "workspace layout was built for another precision");
     const kpd_workspace_layout& L = *layout;
+    KPD_TRY(check_stage(L, B, S, n_max, precision, "kpd_roi_head"));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     const int K = plan->num_keypoints;
@@ -232,6 +245,7 @@ extern "C" int kpd_heatmap_head(const kpd_plan* plan, int precision, const float
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     KPD_CHECK_ARG(n <= layout->max_rois, "kpd_heatmap_head: workspace laid out for %d ROIs, got %d", layout->max_rois, n);
+    KPD_CHECK_ARG(precision == layout->precision, "kpd_heatmap_head: precision %d != %d the workspace layout was built for", precision, layout->precision);
     const ScratchMap sm = scratch_map(L.batch, L.size, L.max_rois + 1);
     nchw_to_roi_kernel<<<dim3(ROI_PARTS, n), 256, 0, s>>>(d_x, reinterpret_cast<float*>(ws + L.roi_feat),
         reinterpret_cast<float*>(ws + L.scratch + sm.roi_part), reinterpret_cast<int32_t*>(ws + L.roi_slot),
@@ -264,6 +278,7 @@ extern "C" int kpd_fpn_levels123(const kpd_plan* plan, int B, int S, void* d_wor
     KPD_TRY(check_layout(plan, d_workspace, layout));
     KPD_CHECK_ARG(d_out != nullptr, "kpd_fpn_levels123: null output table");
     const kpd_workspace_layout& L = *layout;
+    KPD_TRY(check_stage(L, B, S, -1, -1, "kpd_fpn_levels123"));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     const ScratchMap sm = scratch_map(B, S, 1);
@@ -271,7 +286,19 @@ extern "C" int kpd_fpn_levels123(const kpd_plan* plan, int B, int S, void* d_wor
     const int hs[4] = {S / 2, S / 8, S / 16, S / 32};
     for (int i = 1; i < 4; i++) {
         if (!d_out[i]) continue;
-        KPD_TRY(conv_dense_simt(plan->fpn_conv[i], reinterpret_cast<const float*>(ws + L.scratch + lat_off[i]), d_out[i], B, hs[i], hs[i], ACT_RELU, nullptr, s));
+        const float* lat = reinterpret_cast<const float*>(ws + L.scratch + lat_off[i]);
+        if (i == 1) {
+            // the trunk keeps lateral 1 rounded to tf32 (it is an operand of the composed FPN-0 MMA); level 1 of the reference is
+            // plain fp32, so the lateral is recomputed unrounded here (exact CUDA-core GEMM + x2 top-down add) into the
+            // lateral-0 region, which nothing reads after kpd_backbone_fpn0 has finished
+            float* exact = reinterpret_cast<float*>(ws + L.lateral0);
+            PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[1]); a.Wraw = plan->w_lat[1]; a.out = exact;
+            a.M = (int64_t)B * hs[1] * hs[1]; a.K = 24; a.N = 128; a.act = ACT_NONE; a.hw = hs[1] * hs[1]; a.exact = 1;
+            a.res = reinterpret_cast<const float*>(ws + L.scratch + lat_off[2]); a.res_mode = 2; a.H = hs[1]; a.W = hs[1]; a.up = 2;
+            KPD_TRY(pointwise_ffma(a, plan->sm_count, s));
+            lat = exact;
+        }
+        KPD_TRY(conv_dense_simt(plan->fpn_conv[i], lat, d_out[i], B, hs[i], hs[i], ACT_RELU, nullptr, s));
     }
     return 0;
 }

@@ -83,8 +83,12 @@ __global__ void __launch_bounds__(128) scores_topk_kernel(const float* __restric
     const float sv = 1.f / (1.f + expf(-(oa + om)));
     sc[c] = sv; scores[(int64_t)b * 128 + c] = sv;
     __syncthreads();
+    // rank on order-preserving integer keys: a strict total order even when a score is NaN (a NaN ranks above every number),
+    // so the 64 slots are always all written with distinct channels
+    auto key = [](float f) { const uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+    const uint32_t kv = key(sv);
     int rank = 0;
-    for (int j = 0; j < 128; j++) { const float o = sc[j]; rank += (o > sv) || (o == sv && j < c); }
+    for (int j = 0; j < 128; j++) { const uint32_t o = key(sc[j]); rank += (o > kv) || (o == kv && j < c); }
     if (rank < KPD_TOPK) topk[(int64_t)b * KPD_TOPK + rank] = c;
 }
 
@@ -175,3 +179,52 @@ int conv_dense_simt(const DenseConv& c, const float* in, float* out, int N, int 
 }
 
 }  // namespace kpd
+
+// ------------------------------------------------------------------------------------------------
+// Leaf form of ChannelAttention.forward + select_top_k_channels on a caller's NCHW tensor (keypoint_model.py:33-44, :653-661).
+namespace kpd {
+// global avg / max of one (image, channel) plane per CTA; fixed-order tree => deterministic
+__global__ void __launch_bounds__(256) plane_pool_kernel(const float* __restrict__ x, float* __restrict__ avg, float* __restrict__ mx, int HW) {
+    const int plane = blockIdx.y * gridDim.x + blockIdx.x;
+    const float* p = x + (int64_t)plane * HW;
+    float s = 0.f, m = -INFINITY;
+    for (int i = threadIdx.x; i < HW; i += 256) { const float v = __ldg(p + i); s += v; m = fmaxf(m, v); }
+    __shared__ float ss[256], sm[256];
+    ss[threadIdx.x] = s; sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { ss[threadIdx.x] += ss[threadIdx.x + o]; sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { avg[plane] = ss[0] / (float)HW; mx[plane] = sm[0]; }
+}
+// out[b][j] = x[b][topk[b][j]] (planes of HW floats)
+__global__ void __launch_bounds__(256) gather_planes_kernel(const float* __restrict__ x, const int32_t* __restrict__ topk,
+                                                            float* __restrict__ out, int HW) {
+    const int b = blockIdx.y, j = blockIdx.x;
+    const int c = min(max(topk[b * KPD_TOPK + j], 0), KPD_FPN_CH - 1);
+    const float* src = x + ((int64_t)b * KPD_FPN_CH + c) * HW;
+    float* dst = out + ((int64_t)b * KPD_TOPK + j) * HW;
+    for (int i = threadIdx.x; i < HW; i += 256) dst[i] = __ldg(src + i);
+}
+}  // namespace kpd
+
+extern "C" int kpd_channel_attention(const kpd_plan* plan, const float* d_feat_nchw, int batch, int hw, float* d_scores,
+                                     int32_t* d_topk, float* d_selected, void* d_scratch, void* stream) {
+    using namespace kpd;
+    KPD_CHECK_ARG(plan && d_feat_nchw && d_scratch, "kpd_channel_attention: null argument");
+    KPD_CHECK_ARG(batch > 0 && batch <= 65535 && hw > 0, "kpd_channel_attention: bad batch / plane size %d / %d", batch, hw);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float* avg = static_cast<float*>(d_scratch);
+    float* mx = avg + (size_t)batch * KPD_FPN_CH;
+    float* scores = d_scores ? d_scores : mx + (size_t)batch * KPD_FPN_CH;
+    int32_t* topk = d_topk ? d_topk : reinterpret_cast<int32_t*>(mx + 2 * (size_t)batch * KPD_FPN_CH);
+    plane_pool_kernel<<<dim3(KPD_FPN_CH, batch), 256, 0, s>>>(d_feat_nchw, avg, mx, hw);
+    KPD_LAUNCH_CHECK();
+    KPD_TRY(run_scores_topk(plan, batch, avg, mx, scores, topk, s));
+    if (d_selected) {
+        gather_planes_kernel<<<dim3(KPD_TOPK, batch), 256, 0, s>>>(d_feat_nchw, topk, d_selected, hw);
+        KPD_LAUNCH_CHECK();
+    }
+    return 0;
+}

@@ -212,6 +212,11 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
     cudaDeviceProp prop;
     KPD_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) { set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor); return KPD_ERR_UNSUPPORTED; }
+    // the upload below runs on `device`; the caller's current device is restored on every exit path (a plan may be
+    // built for a GPU other than the thread's current one)
+    int prev_device = device;
+    KPD_CUDA(cudaGetDevice(&prev_device));
+    struct DeviceRestore { int prev, cur; ~DeviceRestore() { if (prev != cur) cudaSetDevice(prev); } } device_restore{prev_device, device};
     KPD_CUDA(cudaSetDevice(device));
 
     const int cin0 = desc->in_channels;

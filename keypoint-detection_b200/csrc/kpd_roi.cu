@@ -9,37 +9,52 @@
 namespace kpd {
 
 // ------------------------------------------------------------------------------------------------
-// Order-preserving compaction of the non-zero boxes.  One block; thread b scans image b's P boxes.
+// Order-preserving compaction of the non-zero boxes.  One block; images are walked in chunks of 1024 (thread = image) with a
+// block-wide exclusive scan of the per-image counts and a running carry, so any batch size works without dynamic shared memory.
 __global__ void __launch_bounds__(1024) build_rois_kernel(const float* __restrict__ boxes, int B, int P,
                                                           float* __restrict__ roi_box, int32_t* __restrict__ roi_batch,
                                                           int32_t* __restrict__ roi_slot, int32_t* __restrict__ img_count,
                                                           int32_t* __restrict__ roi_count) {
-    extern __shared__ int32_t cnt[];       // [B] counts -> exclusive offsets
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    __shared__ int32_t warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int b0 = 0; b0 < B; b0 += 1024) {
+        const int b = b0 + tid;
         int c = 0;
-        for (int p = 0; p < P; p++) {
-            const float4 v = reinterpret_cast<const float4*>(boxes)[(int64_t)b * P + p];
-            c += !(v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f);
+        if (b < B) {
+            for (int p = 0; p < P; p++) {
+                const float4 v = reinterpret_cast<const float4*>(boxes)[(int64_t)b * P + p];
+                c += !(v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f);
+            }
+            img_count[b] = c;
         }
-        cnt[b] = c; img_count[b] = c;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int b = 0; b < B; b++) { const int c = cnt[b]; cnt[b] = run; run += c; }
-        *roi_count = run;
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        int n = cnt[b], rank = 0;
-        for (int p = 0; p < P; p++) {
-            const float4 v = reinterpret_cast<const float4*>(boxes)[(int64_t)b * P + p];
-            if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
-            reinterpret_cast<float4*>(roi_box)[n] = v;
-            roi_batch[n] = b; roi_slot[n] = b * P + rank;
-            n++; rank++;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            warp_tot[lane] = w;
         }
+        __syncthreads();
+        int n = carry + incl - c + (warp > 0 ? warp_tot[warp - 1] : 0);
+        carry += warp_tot[31];
+        if (b < B) {
+            int rank = 0;
+            for (int p = 0; p < P; p++) {
+                const float4 v = reinterpret_cast<const float4*>(boxes)[(int64_t)b * P + p];
+                if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+                reinterpret_cast<float4*>(roi_box)[n] = v;
+                roi_batch[n] = b; roi_slot[n] = b * P + rank;
+                n++; rank++;
+            }
+        }
+        __syncthreads();                                   // warp_tot is rewritten by the next chunk
     }
+    if (tid == 0) *roi_count = carry;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -65,7 +80,7 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict_
     const float bin_h = rh / 56.f, bin_w = rw / 56.f;
     const int gh = (int)ceilf(rh / 56.f), gw = (int)ceilf(rw / 56.f);
     const float count = (float)max(gh * gw, 1);
-    const int c0 = topk[b * KPD_TOPK + lane], c1 = topk[b * KPD_TOPK + lane + 32];
+    const int c0 = min(max(topk[b * KPD_TOPK + lane], 0), KPD_FPN_CH - 1), c1 = min(max(topk[b * KPD_TOPK + lane + 32], 0), KPD_FPN_CH - 1);   // (a caller-supplied override cannot index out of the pixel)
     const float* fb = fpn0 + (int64_t)b * H * W * 128;
     float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
     const int row0 = blockIdx.x * 2;
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const float* __restr
     }
     __syncthreads();
     const int xs0 = span[0], ncol = span[1] - span[0] + 1;
-    const int c0 = topk[b * KPD_TOPK + lane], c1 = topk[b * KPD_TOPK + lane + 32];
+    const int c0 = min(max(topk[b * KPD_TOPK + lane], 0), KPD_FPN_CH - 1), c1 = min(max(topk[b * KPD_TOPK + lane + 32], 0), KPD_FPN_CH - 1);   // (a caller-supplied override cannot index out of the pixel)
     const float* fb = fpn0 + (int64_t)b * H * W * 128;
     float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
     for (int r = 0; r < 2; r++) {
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(256) head_att_apply_kernel(const float* __rest
 }
 
 int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
-    build_rois_kernel<<<1, 1024, sizeof(int32_t) * B, s>>>(boxes, B, P, reinterpret_cast<float*>(ws + L.roi_box),
+    build_rois_kernel<<<1, 1024, 0, s>>>(boxes, B, P, reinterpret_cast<float*>(ws + L.roi_box),
         reinterpret_cast<int32_t*>(ws + L.roi_batch), reinterpret_cast<int32_t*>(ws + L.roi_slot),
         reinterpret_cast<int32_t*>(ws + L.img_count), reinterpret_cast<int32_t*>(ws + L.roi_count));
     KPD_LAUNCH_CHECK();

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "kpd_backbone_fpn0": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, _P, C.POINTER(WorkspaceLayout), _P]),
     "kpd_fpn_levels123": (C.c_int, [_P, C.c_int, C.c_int, _P, C.POINTER(WorkspaceLayout), C.POINTER(_P), _P]),
     "kpd_channel_topk": (C.c_int, [_P, C.c_int, _P, C.POINTER(WorkspaceLayout), _P]),
+    "kpd_channel_attention": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "kpd_roi_head": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P,
                                C.POINTER(WorkspaceLayout), _P]),
     "kpd_roi_align": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

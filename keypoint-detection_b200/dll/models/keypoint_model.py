@@ -27,6 +27,34 @@ class ChannelAttention(ParamTree):
     def __init__(self, in_channels, reduction_ratio=16):
         super().__init__(channel_attention_entries(in_channels, reduction_ratio))
         self.in_channels = in_channels
+        self._plans = PlanCache(1, 17)
+
+    def _run(self, x, want_selected):
+        """kpd_channel_attention on x [B,128,H,W] -> (scores [B,128], topk int32 [B,64], selected [B,64,H,W] | None)."""
+        import ctypes as C  # noqa: F401  (pointer helpers live in _native)
+        if self.in_channels != 128:
+            raise NotImplementedError("the CUDA channel attention is built for the model's 128 FPN channels")
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise N.NativeLibraryError("move the module to a CUDA device (no CPU fallback)")
+        if x.dim() != 4 or x.size(1) != 128:
+            raise ValueError(f"expected [B,128,H,W], got {tuple(x.shape)}")
+        state = {"channel_attention." + k: v for k, v in self.state_dict(keep_vars=True).items()}
+        plan = self._plans.get(state, dev)
+        with torch.cuda.device(dev):
+            x = as_cuda_f32(x, dev)
+            B, _, H, W = x.shape
+            scores = torch.empty(B, 128, device=dev, dtype=torch.float32)
+            topk = torch.empty(B, 64, device=dev, dtype=torch.int32)
+            sel = torch.empty(B, 64, H, W, device=dev, dtype=torch.float32) if want_selected else None
+            scratch = torch.empty(B * 512, device=dev, dtype=torch.float32)
+            N.check(N.load().kpd_channel_attention(plan.handle, N.ptr(x), B, H * W, N.ptr(scores), N.ptr(topk), N.ptr(sel),
+                                                   N.ptr(scratch), N.stream_ptr(dev)), "kpd_channel_attention")
+        return scores, topk, sel
+
+    def forward(self, x):
+        """keypoint_model.py:33-44: x [B,C,H,W] -> channel scores [B,C] = sigmoid(MLP(avgpool) + MLP(maxpool))."""
+        return self._run(x, False)[0]
 
 
 class _InferenceOnlyLoss(nn.Module):
@@ -236,6 +264,28 @@ class MultiPersonKeypointModel(nn.Module):
                                                    N.stream_ptr(dev)), "kpd_roi_align")
                     outs.append(o[..., :min(64, cs - h0)].permute(0, 3, 1, 2))
         return torch.cat(outs, dim=1)
+
+
+def select_top_k_channels(features, channel_attention, k=64):
+    """keypoint_model.py:653-661: the k best-scoring channels of features [B,C,H,W] in descending score order
+    -> [B,k,H,W].  (The fused forward never materialises this tensor: the indices go straight to ROI-align.)"""
+    if k != 64 or features.size(1) != 128:
+        raise NotImplementedError("the CUDA selection kernel is built for the model's top-64 of 128 channels")
+    return channel_attention._run(features, True)[2]
+
+
+def parse_ground_truth(file_path):
+    """keypoint_model.py:587-628: first line of a YOLO-pose label file `class cx cy w h (x y v)*K` ->
+    {'bboxes': [Tensor[1,4]], 'keypoints': Tensor[1,1,K,2], 'visibilities': Tensor[1,1,K]}."""
+    with open(file_path, 'r') as f:
+        data = f.readline().strip().split()
+    bbox = torch.tensor([float(v) for v in data[1:5]])
+    num_keypoints = (len(data) - 5) // 3
+    kp = [[float(data[5 + 3 * i]), float(data[6 + 3 * i])] for i in range(num_keypoints)]
+    vis = [int(data[7 + 3 * i]) for i in range(num_keypoints)]
+    return {'bboxes': [bbox.unsqueeze(0)],
+            'keypoints': torch.tensor(kp).reshape(1, 1, num_keypoints, 2),
+            'visibilities': torch.tensor(vis).reshape(1, 1, num_keypoints)}
 
 
 def box_center_to_corners(box):

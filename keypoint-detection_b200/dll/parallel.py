@@ -58,9 +58,38 @@ def gather_outputs(local: Dict, global_batch: int, group=None, gather_heatmap: b
     return out
 
 
+def _persons(batch: Dict) -> int:
+    """Padded person count P of the global batch (0 when no boxes are supplied)."""
+    b = batch.get('bboxes') if isinstance(batch, dict) else None
+    if isinstance(b, list) and len(b) > 0 and torch.is_tensor(b[0]):
+        return int(b[0].size(-2)) if b[0].dim() >= 2 else 0
+    if torch.is_tensor(b) and b.dim() == 3:
+        return int(b.size(1))
+    return 0
+
+
+def _empty_shard_result(model, batch: Dict) -> Dict:
+    """Result of a rank whose shard holds no image: zero rows with the trailing shapes the other ranks produce
+    ([b,P,1,K,2] / [b,P,1,K,3] / [b,P,K,56,56]; the reference's rank-changing no-box shapes when P == 0), so the
+    gather sees tensors that differ in dim 0 only.  The model is not called (its 0-image path has other shapes)."""
+    K = int(getattr(model, 'num_keypoints', 17))
+    try:
+        dev = next(model.parameters()).device
+    except (AttributeError, StopIteration, TypeError):
+        dev = batch['image'].device
+    P = _persons(batch)
+    if P == 0:
+        return {'keypoints': torch.zeros(0, 1, K, 2, device=dev), 'visibilities': torch.zeros(0, 1, K, device=dev),
+                'heatmap': torch.zeros(0, 1, K, 56, 56, device=dev), 'boxes': []}
+    return {'keypoints': torch.zeros(0, P, 1, K, 2, device=dev), 'visibilities': torch.zeros(0, P, 1, K, 3, device=dev),
+            'heatmap': torch.zeros(0, P, K, 56, 56, device=dev), 'boxes': []}
+
+
 @torch.no_grad()
-def predict_data_parallel(model, batch: Dict, group=None, gather_heatmap: bool = False) -> Dict:
-    """Every rank passes the same global batch (or at least its own slice); returns the gathered global result.
+def predict_data_parallel(model, batch: Dict, group=None, gather_heatmap: bool = False, presharded: bool = False,
+                          global_batch: Optional[int] = None) -> Dict:
+    """Every rank passes the same global batch (default), or -- `presharded=True` -- only its own contiguous slice of a
+    `global_batch`-image batch split by `shard_bounds`; returns the gathered global result plus the rank's own under 'local'.
 
     Works with any backend torch.distributed offers: NCCL on the GPUs (product path), gloo in the CPU unit tests
     (with a stand-in `model` callable -- the CUDA model itself has no CPU path).
@@ -68,8 +97,19 @@ def predict_data_parallel(model, batch: Dict, group=None, gather_heatmap: bool =
     if not dist.is_initialized():
         return model.predict(batch) if hasattr(model, 'predict') else model(batch)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    local = shard_batch(batch, rank, world)
-    res = model.predict(local) if hasattr(model, 'predict') else model(local)
-    out = gather_outputs(res, batch['image'].size(0), group, gather_heatmap)
+    if presharded:
+        if global_batch is None:
+            raise ValueError("presharded=True needs global_batch (the image count over all ranks)")
+        lo, hi = shard_bounds(global_batch, rank, world)
+        if batch['image'].size(0) != hi - lo:
+            raise ValueError(f"rank {rank} owns images [{lo}, {hi}) of {global_batch} but was given {batch['image'].size(0)}")
+        local, total = batch, global_batch
+    else:
+        local, total = shard_batch(batch, rank, world), batch['image'].size(0)
+    if local['image'].size(0) == 0:
+        res = _empty_shard_result(model, batch)         # global batch < world size: this rank owns no image
+    else:
+        res = model.predict(local) if hasattr(model, 'predict') else model(local)
+    out = gather_outputs(res, total, group, gather_heatmap)
     out['local'] = res
     return out

@@ -27,17 +27,22 @@ def _worker(rank, world, port, batch_size, q):
     from dll.parallel import predict_data_parallel, shard_bounds
     g = torch.Generator().manual_seed(0)
     batch = {'image': torch.randn(batch_size, 1, 8, 8, generator=g), 'bboxes': torch.rand(batch_size, 3, 4, generator=g)}
-    out = predict_data_parallel(_stand_in, batch, gather_heatmap=True)
+    small = batch_size < world                 # a rank without images: its empty result carries the model's 56x56 heat-map shape
+    out = predict_data_parallel(_stand_in, batch, gather_heatmap=not small)
     full = _stand_in(batch)
-    ok = all(torch.equal(out[k], full[k]) for k in ('keypoints', 'visibilities', 'heatmap'))
+    ok = all(torch.equal(out[k], full[k]) for k in (('keypoints', 'visibilities') if small else ('keypoints', 'visibilities', 'heatmap')))
     lo, hi = shard_bounds(batch_size, rank, world)
     ok = ok and out['local']['keypoints'].shape[0] == hi - lo
+    # pre-sharded form (what bench.py runs at N > 1): the rank passes only its own slice
+    mine = {'image': batch['image'][lo:hi], 'bboxes': batch['bboxes'][lo:hi]}
+    out2 = predict_data_parallel(_stand_in, mine, gather_heatmap=not small, presharded=True, global_batch=batch_size)
+    ok = ok and torch.equal(out2['keypoints'], full['keypoints']) and torch.equal(out2['visibilities'], full['visibilities'])
     q.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("batch_size", [8, 7])
+@pytest.mark.parametrize("batch_size", [8, 7, 1])
 def test_two_rank_shard_and_gather(batch_size):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
