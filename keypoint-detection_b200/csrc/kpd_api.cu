@@ -15,7 +15,7 @@ struct DecodeArgs {
 int run_decode(const DecodeArgs& a, int dtype, int sm_count, cudaStream_t s);
 int run_dummy_person(const int32_t* img_count, float* vis, int B, int P, int K, cudaStream_t s);
 int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_roi_align(int B, int S, int n_max, const int32_t* topk, int feat_bf16, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int conv_dense_umma_halo(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
                          int out_cm, int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s);
@@ -127,6 +127,16 @@ static int run_head_stack(const kpd_plan* plan, int precision, int B_for_scratch
         ProfScope ps("head_conv2", s);
         KPD_TRY(dense_conv(plan, plan->head_conv[1], precision, use_bf16, ws + L.head_a, ws + L.head_b, n_max, 56, 56, 1, n_valid, s));
     }
+    const int32_t* slot = reinterpret_cast<const int32_t*>(ws + L.roi_slot);
+    if (precision != KPD_PREC_FP32_SIMT) {
+        // conv 256 -> 64 with final_layer[3] (1x1 64 -> 17) + sigmoid fused into its epilogue: the heat maps are computed from
+        // the fp32 accumulators and written straight into the padded output; head_c is never materialised
+        ProfScope ps("head_conv3", s);
+        const FinalFuse fin{plan->w_final, plan->b_final, d_heatmap, slot};
+        KPD_TRY(conv_dense_umma(plan, plan->head_conv[2], use_bf16, ws + L.head_b, ws + L.head_c, use_bf16, n_max, 56, 56, ACT_RELU, 0, n_valid, s,
+                                nullptr, nullptr, 1, &fin));
+        return 0;
+    }
     {
         ProfScope ps("head_conv3", s);
         KPD_TRY(dense_conv(plan, plan->head_conv[2], precision, use_bf16, ws + L.head_b, ws + L.head_c, n_max, 56, 56, 0, n_valid, s));
@@ -134,9 +144,7 @@ static int run_head_stack(const kpd_plan* plan, int precision, int B_for_scratch
     {
         ProfScope ps("head_final", s);
         dim3 grid((56 * 56 + 127) / 128, n_max);
-        const int32_t* slot = reinterpret_cast<const int32_t*>(ws + L.roi_slot);
-        if (use_bf16) head_final_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(ws + L.head_c), plan->w_final, plan->b_final, slot, n_valid, d_heatmap);
-        else head_final_kernel<float><<<grid, 128, 0, s>>>(reinterpret_cast<const float*>(ws + L.head_c), plan->w_final, plan->b_final, slot, n_valid, d_heatmap);
+        head_final_kernel<float><<<grid, 128, 0, s>>>(reinterpret_cast<const float*>(ws + L.head_c), plan->w_final, plan->b_final, slot, n_valid, d_heatmap);
         KPD_LAUNCH_CHECK();
     }
     return 0;
@@ -157,10 +165,11 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     KPD_TRY(check_stage(L, B, S, -1, precision, "kpd_backbone_fpn0"));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
-    // FPN level 0: composed tcgen05 form (kpd_fpn0.cu; lateral 0 never materialised) unless strict fp32 or KPD_FPN0_CLASSIC=1
-    static const bool classic = getenv("KPD_FPN0_CLASSIC") != nullptr;
+    // FPN level 0: composed tcgen05 form (kpd_fpn0.cu; lateral 0 never materialised) in the fp32 / bf16 modes; the strict
+    // mode materialises lateral 0 and runs the fp32 CUDA-core conv.  bf16 mode stores the map as bf16 (half the write here and
+    // half the ROI-align read; the channel-attention pools still come from the fp32 accumulators).
     const bool strict = precision == KPD_PREC_FP32_SIMT;
-    const bool composed = !strict && !classic;
+    const bool composed = !strict;
     KPD_TRY(run_body(plan, d_images, B, S, strict, composed, ws, L, s));
     KPD_TRY(run_fpn_laterals(plan, B, S, !strict, strict, composed, ws, L, s));
     const ScratchMap sm = scratch_map(B, S, 1);
@@ -170,24 +179,17 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
         {
             ProfScope ps("fpn0_conv", s);
             KPD_TRY(fpn0_fused(plan, reinterpret_cast<const float*>(ws + L.scratch + sm.f0_tf32), reinterpret_cast<const float*>(ws + L.scratch + sm.lat1),
-                               reinterpret_cast<float*>(ws + L.fpn0), pool_part, B, S, s));
+                               ws + L.fpn0, precision == KPD_PREC_BF16 ? 1 : 0, pool_part, B, S, s));
         }
         KPD_TRY(run_pool_final(pool_part, B, fpn0_fused_parts(S), H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg), reinterpret_cast<float*>(ws + L.pool_max), s));
         return 0;
     }
-    const bool fuse_pool = !strict && (H0 % 16 == 0) && (H0 % 8 == 0);
     {
         ProfScope ps("fpn0_conv", s);
-        if (fuse_pool)      // avg/max pooling for the channel scores is reduced in the conv epilogue (fp32 accumulators)
-            KPD_TRY(conv_dense_umma(plan, plan->fpn_conv[0], 0, ws + L.lateral0, ws + L.fpn0, 0, B, H0, H0, ACT_RELU, 0, nullptr, s, pool_part));
-        else
-            KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, H0, H0, 0, nullptr, s));
+        KPD_TRY(dense_conv(plan, plan->fpn_conv[0], precision, 0, ws + L.lateral0, ws + L.fpn0, B, H0, H0, 0, nullptr, s));
     }
-    if (fuse_pool)
-        KPD_TRY(run_pool_final(pool_part, B, (H0 / 16) * (H0 / 8), H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg), reinterpret_cast<float*>(ws + L.pool_max), s));
-    else
-        KPD_TRY(run_pools(reinterpret_cast<const float*>(ws + L.fpn0), B, H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg),
-                          reinterpret_cast<float*>(ws + L.pool_max), pool_part, s));
+    KPD_TRY(run_pools(reinterpret_cast<const float*>(ws + L.fpn0), B, H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg),
+                      reinterpret_cast<float*>(ws + L.pool_max), pool_part, s));
     return 0;
 }
 
@@ -224,7 +226,7 @@ extern "C" int kpd_roi_head(const kpd_plan* plan, int precision, int B, int S, c
     KPD_CUDA(cudaMemsetAsync(d_keypoints, 0, sizeof(float) * (size_t)n_max * K * 2, s));
     KPD_CUDA(cudaMemsetAsync(d_visibilities, 0, sizeof(float) * (size_t)n_max * K * 3, s));
     KPD_TRY(run_build_rois(d_boxes, B, P, ws, L, s));
-    KPD_TRY(run_roi_align(B, S, n_max, topk, ws, L, s));
+    KPD_TRY(run_roi_align(B, S, n_max, topk, precision == KPD_PREC_BF16 ? 1 : 0, ws, L, s));
     KPD_TRY(run_head_stack(plan, precision, B, S, n_max, ws, L, d_heatmap, s));
     DecodeArgs a{};
     a.hm = d_heatmap; a.maps = (int64_t)n_max * K; a.K = K; a.H = 56; a.W = 56; a.inv_temp = 1.f;

@@ -562,19 +562,10 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
         KPD_TRY(pointwise_mma(a, p->sm_count, s));
     }
     if (composed) return 0;
-    // lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add: CUDA-core streaming kernel (exact fp32, rounded to tf32 when it
-    // feeds the kind::tf32 FPN-0 MMA).  KPD_LATERAL0_UMMA=1 selects the tcgen05 variant (kind::tf32, 64-byte swizzled K rows,
-    // residual added in the epilogue): measured no faster (its row-per-thread fp32 epilogue stores 512 B/pixel in 16-byte
-    // pieces) and its single-pass tf32 inputs cost score accuracy (1.2e-5 vs 3e-6), so it is not the default.
-    static const bool umma = getenv("KPD_LATERAL0_UMMA") != nullptr;
-    if (umma && !strict_fp32 && hs[0] % 16 == 0) {
-        KPD_TRY(conv_dense_umma(p, p->lat0_conv, 0, ws + L.feat[0], lat[0], 0, B, hs[0], hs[0], ACT_NONE, round_tf32, nullptr, s,
-                                nullptr, lat[1], hs[0] / hs[1]));
-    } else {
-        ProfScope ps0("fpn_laterals.lat0", s);
-        KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
-                                hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
-    }
+    // strict mode only: lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add, materialised by a CUDA-core streaming kernel
+    ProfScope ps0("fpn_laterals.lat0", s);
+    KPD_TRY(launch_lateral0(reinterpret_cast<const float*>(ws + L.feat[0]), p->w_lat[0], lat[1], lat[0], (int64_t)B * hs[0] * hs[0],
+                            hs[0], hs[0], hs[0] / hs[1], round_tf32, p->sm_count, s));
     return 0;
 }
 

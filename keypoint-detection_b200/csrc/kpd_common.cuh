@@ -119,6 +119,7 @@ struct kpd_plan {
     const float *w_final, *b_final;                    // [64][17], [17]
     // person heads
     const float *w_box[4], *b_box[4], *w_cls[4], *b_cls[4];   // [128][36],[36],[128][9],[9]
+    const float *wu_heads[4], *b_heads[4];                    // box | cls heads side by side, padded to 48 columns: tf32 hi / lo split (kpd_pwu.cu) + bias [48]
 };
 
 namespace kpd {
@@ -131,16 +132,18 @@ ScratchMap scratch_map(int B, int S, int n_rois);
 // ---- launchers implemented across the .cu files (all enqueue on `s`, return 0 / cudaError) ----
 int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, int composed, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, float* out, float* pool_part, int B, int S, cudaStream_t s);
+int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, void* out, int out_bf16, float* pool_part, int B, int S, cudaStream_t s);
 int fpn0_fused_parts(int S);
 int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* scratch, cudaStream_t s);
 int run_pool_final(const float* partials, int B, int parts, int HW, float* avg, float* mx, cudaStream_t s);
 int run_scores_topk(const kpd_plan* p, int B, const float* avg, const float* mx, float* scores, int32_t* topk, cudaStream_t s);
 int conv_dense_simt(const DenseConv& c, const float* in, float* out, int N, int H, int W, int act,
                     const int32_t* n_valid, cudaStream_t s);
+// final_layer[3] (1x1 conv 64 -> 17 + bias) + sigmoid fused into the epilogue of the 64-channel head conv (kpd_conv_umma.cu)
+struct FinalFuse { const float* w; const float* b; float* out; const int32_t* slot; };   // [64][17], [17], heat maps [slot][17][H][W], slot per instance
 int conv_dense_umma(const kpd_plan* p, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
                     int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s,
-                    float* pool_part = nullptr, const float* res = nullptr, int res_up = 1);
+                    float* pool_part = nullptr, const float* res = nullptr, int res_up = 1, const FinalFuse* fin = nullptr);
 int pointwise(const float* in, const float* w, const float* bias, float* out, int64_t pixels, int cin, int cout,
               int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s);
 // Batch-wide pointwise (1x1) convolution as a GEMM over all pixels: out[M][N] = act(A[M][K] * W[K][N] + bias) (+ residual).
@@ -154,6 +157,7 @@ struct PwMma {
     const float* Wraw;                       // [K][N] row-major fp32 (CUDA-core FFMA GEMM, kpd_pwf.cu)
     const float* Wu;                         // [2][Np][Kp] tf32 hi / lo split, K-major rows (tcgen05 3xTF32 GEMM, kpd_pwu.cu)
     int exact;                               // 1: strict-fp32 mode -- CUDA-core FFMA GEMM only
+    float* out2; int split, n2;              // tcgen05 kernel only: columns [0, split) go to out [M][split], columns [split, split + n2) to out2 [M][n2]
 };
 int pointwise_umma(const PwMma& p, int sm_count, cudaStream_t s);
 void pwu_chunks(int N, int* nchunks, int* Nc);

@@ -31,7 +31,13 @@ struct ConvParams {
     const float* bias;
     void* out;                         // NHWC [N,H,W,Cout], bf16 or fp32
     const int32_t* n_valid;            // optional device count of live instances (<= N)
+    // optional fused tail of the heat-map head (Cout == 64): final_layer[3] 1x1 conv 64 -> 17 + bias + sigmoid
+    // (heatmap_head.py:40-44,111) evaluated on the fp32 accumulators after bias + ReLU and written as NCHW fp32 maps
+    // [slot][17][H][W]; the conv's own NHWC output is then not stored at all.
+    const float* fin_w; const float* fin_b;   // [64][17], [17]
+    float* fin_out; const int32_t* fin_slot;  // heat maps; output slot of each instance
 };
+constexpr int FIN_K = 17, FIN_KP = 20;   // joints; padded row of the shared-memory copy (float4 broadcast loads)
 
 // Store 32 consecutive output channels (c0..c0+31) of pixel (n,h,w): NHWC bf16 / fp32, or chunk-major (16-byte chunks).
 __device__ __forceinline__ void epi_store(const ConvParams& p, const float (&v)[32], int n, int h, int w, size_t pix, int c0) {
@@ -98,6 +104,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
     float* red = sbias + p.Cout;                      // pooling only: [4 warps][32][33] transpose tiles
     float* wred = red + 4 * 32 * 33;                  // pooling only: [4 warps][2][Cout] per-warp channel sum / max
+    float* finw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sbias + p.Cout) + 15) & ~uintptr_t(15));   // fused final 1x1 only: [64][FIN_KP] + bias [FIN_KP]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -117,6 +124,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
+    if (p.fin_w) {
+        for (int i = threadIdx.x; i < 65 * FIN_KP; i += blockDim.x) {
+            const int c = i / FIN_KP, k = i - c * FIN_KP;
+            finw[i] = k < FIN_K ? (c < 64 ? p.fin_w[c * FIN_K + k] : p.fin_b[k]) : 0.f;
+        }
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -209,6 +222,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool valid = (w < p.W) && (h < p.H) && (n < n_live);
             const size_t pix = ((size_t)n * p.H + h) * p.W + w;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((acc * MT + ti) * p.Cout);
+            if (p.fin_w) {
+                // fused final_layer[3] + sigmoid: the thread owns one pixel, its 64 conv outputs arrive as two 32-column TMEM
+                // loads, the 17 joint logits accumulate in registers (weights = shared-memory float4 broadcasts) and leave as
+                // 17 NCHW stores (a warp covers 4 rows x 8 pixels of every joint plane: full 32-byte sectors)
+                float a[FIN_KP];
+#pragma unroll
+                for (int k = 0; k < FIN_KP; k++) a[k] = finw[64 * FIN_KP + k];
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t r[32];
+                    tc_ld32(taddr + c0, r);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float x = fmaxf(__uint_as_float(r[j]) + sbias[c0 + j], 0.f);
+                        const float4* wp = reinterpret_cast<const float4*>(finw + (c0 + j) * FIN_KP);
+#pragma unroll
+                        for (int q = 0; q < FIN_KP / 4; q++) {
+                            const float4 w4 = wp[q];
+                            a[4 * q + 0] = fmaf(x, w4.x, a[4 * q + 0]); a[4 * q + 1] = fmaf(x, w4.y, a[4 * q + 1]);
+                            a[4 * q + 2] = fmaf(x, w4.z, a[4 * q + 2]); a[4 * q + 3] = fmaf(x, w4.w, a[4 * q + 3]);
+                        }
+                    }
+                }
+                if (valid) {
+                    float* o = p.fin_out + ((size_t)p.fin_slot[n] * FIN_K * p.H + h) * p.W + w;
+                    const size_t plane = (size_t)p.H * p.W;
+#pragma unroll
+                    for (int k = 0; k < FIN_K; k++) o[k * plane] = 1.f / (1.f + expf(-a[k]));
+                }
+                continue;
+            }
             for (int c0 = cbeg; c0 < cend; c0 += 32) {
                 uint32_t r[32];
                 tc_ld32(taddr + c0, r);
@@ -429,7 +473,7 @@ conv_umma_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // ------------------------------------------------------------------------------------------------ host side
 int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
                     int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s, float* pool_part,
-                    const float* res, int res_up) {
+                    const float* res, int res_up, const FinalFuse* fin) {
     if (N <= 0) return 0;
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
@@ -443,6 +487,10 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     p.tiles_w = (W + p.tw - 1) / p.tw; p.tiles_h = (H + p.th - 1) / p.th; p.tiles_n = (N + p.tn - 1) / p.tn;
     p.act = act; p.round_out_tf32 = round_out_tf32; p.out_bf16 = out_bf16; p.bias = c.bias; p.out = out; p.n_valid = n_valid;
     p.pool_part = pool_part; p.row_bytes = row_bytes; p.res = res; p.res_up = res_up > 0 ? res_up : 1;
+    if (fin) {
+        if (c.cout != 64 || pool_part || res) { set_error("conv_dense_umma: the fused final 1x1 needs a plain 64-channel conv"); return KPD_ERR_UNSUPPORTED; }
+        p.fin_w = fin->w; p.fin_b = fin->b; p.fin_out = fin->out; p.fin_slot = fin->slot;
+    }
     static const int mt_env = getenv("KPD_CONV_MT") ? atoi(getenv("KPD_CONV_MT")) : 0;
     int mt = 1;                                          // M-tiles per weight stage: as many as TMEM (512 columns, double-buffered) allows, <= 4
     while (mt < 4 && 2 * (mt * 2) * c.cout <= 512) mt *= 2;
@@ -451,7 +499,7 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     p.mt = mt;
     if (pool_part && p.tn != 1) { set_error("conv_dense_umma: fused pooling needs W %% 16 == 0 and H %% 8 == 0"); return KPD_ERR_UNSUPPORTED; }
     const int stage_bytes = mt * 128 * row_bytes + c.cout * row_bytes;
-    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0);
+    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0) + (fin ? 4 * 65 * FIN_KP + 16 : 0);
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
     p.stages = stages;

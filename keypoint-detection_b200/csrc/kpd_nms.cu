@@ -109,6 +109,15 @@ extern "C" int kpd_person_heads(const kpd_plan* plan, int level, const float* d_
     KPD_CHECK_ARG(level >= 0 && level < 4, "kpd_person_heads: level must be 0..3");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ProfScope ps("person_heads", s);
+    KPD_CHECK_ARG(pixels > 0, "kpd_person_heads: pixels must be > 0");
+    if (d_box_out && d_cls_out && pixels < ((int64_t)1 << 31) - 128) {
+        // both heads as one tcgen05 GEMM [pixels x 128] x [128 x 48] with the on-chip 3xTF32 split (fp32-level accuracy);
+        // the epilogue routes the 36 box and 9 class columns to their own tensors, the feature map is read once
+        PwMma a{};
+        a.A = d_feat_nhwc; a.Wu = plan->wu_heads[level]; a.bias = plan->b_heads[level]; a.out = d_box_out; a.out2 = d_cls_out; a.split = 36; a.n2 = 9;
+        a.M = pixels; a.K = 128; a.N = 48; a.act = ACT_NONE; a.hw = 1;
+        return pointwise_umma(a, plan->sm_count, s);
+    }
     if (d_box_out) KPD_TRY(pointwise_ex(d_feat_nhwc, plan->w_box[level], plan->b_box[level], d_box_out, pixels, 128, 36, ACT_NONE, 1, 0, s));
     if (d_cls_out) KPD_TRY(pointwise_ex(d_feat_nhwc, plan->w_cls[level], plan->b_cls[level], d_cls_out, pixels, 128, 9, ACT_NONE, 1, 0, s));
     return 0;

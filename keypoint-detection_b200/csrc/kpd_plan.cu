@@ -334,13 +334,22 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         }
     }
     c.skip();   // person_detector.anchors (never read by the reference forward, person_head.py:141-166)
+    size_t off_box[4], off_bbox[4];
     for (int i = 0; i < 4; i++) {
         const float* w = c.next(); const float* b = c.next();
         pack_conv_kc(B, w, b, nullptr, 0, 36, 128, 1, ow, ob); reg(&p->w_box[i], ow); reg(&p->b_box[i], ob);
+        off_box[i] = ow; off_bbox[i] = ob;
     }
     for (int i = 0; i < 4; i++) {
         const float* w = c.next(); const float* b = c.next();
         pack_conv_kc(B, w, b, nullptr, 0, 9, 128, 1, ow, ob); reg(&p->w_cls[i], ow); reg(&p->b_cls[i], ob);
+        // both heads of the level as ONE [128][48] matrix (36 box | 9 cls | 3 zero columns) for the tcgen05 GEMM
+        const size_t oc = B.alloc(sizeof(float) * 128 * 48), obias = B.alloc(sizeof(float) * 48);
+        for (int k = 0; k < 128; k++)
+            for (int n = 0; n < 48; n++)
+                B.f(oc)[k * 48 + n] = n < 36 ? B.f(off_box[i])[k * 36 + n] : (n < 45 ? B.f(ow)[k * 9 + n - 36] : 0.f);
+        for (int n = 0; n < 48; n++) B.f(obias)[n] = n < 36 ? B.f(off_bbox[i])[n] : (n < 45 ? B.f(ob)[n - 36] : 0.f);
+        reg(&p->wu_heads[i], pack_umma_split(B, oc, 128, 48)); reg(&p->b_heads[i], obias);
     }
     {   // heatmap head attention: Linear weights kept in their [out][in] form
         const float* w0 = c.next(); const float* b0 = c.next(); const float* w2 = c.next(); const float* b2 = c.next();

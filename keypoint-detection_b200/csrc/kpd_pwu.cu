@@ -24,6 +24,7 @@ struct PwUParams {
     const float* bias; float* out; const float* res; const float* se_scale;
     uint32_t M; int K, N, Nc, nchunks, tiles_m, total, stages, stage_bytes;
     int act, hw, res_mode, H, W, up, round_tf32, Np;
+    float* out2; int split, n2;       // optional two-tensor output: columns [0, split) -> out [M][split], [split, split + n2) -> out2 [M][n2]
 };
 
 constexpr int PU_EPI_WARPS = 8, PU_THREADS = 192 + 32 * PU_EPI_WARPS, PU_RS = 36, PU_MAXN = 640;
@@ -210,6 +211,16 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
                                 }
                                 if (p.round_tf32) { x.x = tf32_rna(x.x); x.y = tf32_rna(x.y); x.z = tf32_rna(x.z); x.w = tf32_rna(x.w); }
+                                if (p.out2) {                               // person heads: box | cls columns to two row-major tensors
+                                    const size_t m = ooff[it] / (size_t)p.N;
+                                    if (n < p.split) *reinterpret_cast<float4*>(p.out + m * p.split + n) = x;
+                                    else {
+                                        float* o2 = p.out2 + m * p.n2 + (n - p.split);
+                                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                                        for (int e = 0; e < 4; e++) if (n - p.split + e < p.n2) o2[e] = xs[e];
+                                    }
+                                } else
                                 *reinterpret_cast<float4*>(p.out + ooff[it] + n) = x;
                             }
                         }
@@ -259,6 +270,7 @@ int pointwise_umma(const PwMma& a, int sm_count, cudaStream_t s) {
     const int64_t total = (int64_t)p.tiles_m * p.nchunks;
     if (total >= ((int64_t)1 << 31)) { set_error("pointwise_umma: too many tiles"); return KPD_ERR_UNSUPPORTED; }
     p.total = (int)total;
+    p.out2 = a.out2; p.split = a.split; p.n2 = a.n2;
     p.act = a.act; p.hw = a.hw > 0 ? a.hw : 1; p.res_mode = a.res ? a.res_mode : 0; p.H = a.H; p.W = a.W; p.up = a.up > 0 ? a.up : 1; p.round_tf32 = a.round_tf32;
     p.stage_bytes = 2 * PU_A + 2 * p.Nc * 128;
     const int misc = 1024 /*align*/ + 8 * (3 * 8 + 4) + 32 + 4 * PU_MAXN + 4 * (PU_EPI_WARPS * 32 * PU_RS) + 64;
