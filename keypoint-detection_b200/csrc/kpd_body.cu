@@ -333,18 +333,32 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
     }
     const float* cur = feat[0];
     int H = S / 2;
+    static const bool no_ed = getenv("KPD_NO_ED") != nullptr;      // A/B timing: the layer-by-layer expand GEMM + depthwise kernels
     for (int i = 0; i < 11; i++) {
         const MBBlock& m = p->blocks[i];
         const int Ho = H / m.stride;
         const float* x = cur;
-        if (m.w_exp) {
-            PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.Wu = m.wu_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act; a.exact = strict_fp32;
-            ProfScope ps("body.pointwise", s);
-            KPD_TRY(pointwise_mma(a, p->sm_count, s));
-            x = expand;
-        }
         int pool_parts = 1;
-        { ProfScope ps("body.depthwise", s); KPD_TRY(depthwise_batched(m, x, dwout, m.se ? se_pool : nullptr, sm.se_pool_floats, &pool_parts, B, H, p->sm_count, s)); }
+        bool fused = false;
+        if (m.w_exp && !strict_fp32 && !no_ed) {
+            // expand + depthwise (+ squeeze partials) in one kernel, the expanded tensor stays on chip (kpd_ed.cu); layers whose
+            // bands do not fit an SM (wide maps of large inputs) fall through to the two-kernel form below
+            ProfScope ps("body.expand_dw", s);
+            static const char* tags[11] = {"ed.f1", "ed.f2", "ed.f3", "ed.f4", "ed.f5", "ed.f6", "ed.f7", "ed.f8", "ed.f9", "ed.f10", "ed.f11"};
+            ProfScope ps2(tags[i], s);
+            const int r = expand_depthwise_fused(m, cur, dwout, m.se ? se_pool : nullptr, sm.se_pool_floats, &pool_parts, B, H, p->sm_count, s);
+            if (r == 0) fused = true; else if (r != KPD_ERR_UNSUPPORTED) return r;
+        }
+        if (!fused) {
+            if (m.w_exp) {
+                PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.Wu = m.wu_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act; a.exact = strict_fp32;
+                ProfScope ps("body.pointwise", s);
+                KPD_TRY(pointwise_mma(a, p->sm_count, s));
+                x = expand;
+            }
+            ProfScope ps("body.depthwise", s);
+            KPD_TRY(depthwise_batched(m, x, dwout, m.se ? se_pool : nullptr, sm.se_pool_floats, &pool_parts, B, H, p->sm_count, s));
+        }
         if (m.se) {
             ProfScope ps("body.se", s);
             KPD_TRY(launch_se_fc(m, se_pool, pool_parts, se_scale, B, 1.f / (float)(Ho * Ho), s));

@@ -78,6 +78,9 @@ struct MBBlock {
     // the same 1x1 weights pre-split for 3xTF32 mma.sync (m16n8k8 B fragments): float4 [K/8][N/8][32 lanes] =
     // (b0_hi, b1_hi, b0_lo, b1_lo), b0 = W[k0+t][n0+g], b1 = W[k0+t+4][n0+g], g = lane>>2, t = lane&3
     const float4 *wf_exp, *wf_proj;
+    // fused expand + depthwise kernel (kpd_ed.cu): expand weights as tf32 hi / lo rows [2][ceil(exp/32)*32][slabs * row floats]
+    // (K-major, zero padded) and per 32-channel chunk one block [2 + k*k][32] = expand bias | depthwise bias | tap rows
+    const float *wed_exp, *ed_params;
 };
 
 struct DenseConv {          // 3x3 (or 1x1) dense conv, BN folded
@@ -160,6 +163,9 @@ struct PwMma {
     float* out2; int split, n2;              // tcgen05 kernel only: columns [0, split) go to out [M][split], columns [split, split + n2) to out2 [M][n2]
 };
 int pointwise_umma(const PwMma& p, int sm_count, cudaStream_t s);
+void ed_operand_shape(int K, int* RB, int* slabs);
+int expand_depthwise_fused(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts,
+                           int B, int H, int sm_count, cudaStream_t s);
 void pwu_chunks(int N, int* nchunks, int* Nc);
 int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s);
 int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s);

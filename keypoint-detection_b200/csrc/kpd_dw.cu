@@ -131,6 +131,10 @@ __global__ void __launch_bounds__(DW_THREADS, 2) dw_tma_kernel(const __grid_cons
                             for (int kx = 0; kx < K; kx++)
 #pragma unroll
                                 for (int j = 0; j < XR; j++) acc[j] = fmaf(win[(r * S + ky) % K][j * S + kx], w[ky * K + kx], acc[j]);
+                        // all XR chains are complete HERE: without this the compiler sinks each k*k-FMA chain into its own
+                        // `j < nvalid` branch, where it runs as one dependent chain (4 cycles per FMA instead of 1)
+#pragma unroll
+                        for (int j = 0; j < XR; j++) asm volatile("" : "+f"(acc[j]));
                         if (active) {
                             float* orow = op + i * opitch;
 #pragma unroll

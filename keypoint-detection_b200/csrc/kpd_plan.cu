@@ -240,9 +240,11 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         m.se = kBlocks[i][4]; m.act = kBlocks[i][5]; m.stride = kBlocks[i][6];
         m.res = (m.stride == 1 && m.cin == m.cout);
         m.sq = m.se ? make_divisible(m.exp / 4, 8) : 0;
+        size_t o_wexp = 0, o_bexp = 0;
         if (m.exp != m.cin) {
             const float* w = c.next(); BN bn = read_bn(c);
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.exp, m.cin, 1, ow, ob);
+            o_wexp = ow; o_bexp = ob;
             reg(&m.w_exp, ow); reg(&m.b_exp, ob);
             reg(&m.wf_exp, pack_mma_frag(B, ow, m.cin, m.exp));
             reg(&m.wu_exp, pack_umma_split(B, ow, m.cin, m.exp));
@@ -256,6 +258,27 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
                 B.f(ob)[ch] = (float)sh[ch];
             }
             reg(&m.w_dw, ow); reg(&m.b_dw, ob);
+            if (m.exp != m.cin) {   // operands of the fused expand + depthwise kernel (kpd_ed.cu)
+                int RB, slabs; kpd::ed_operand_shape(m.cin, &RB, &slabs);
+                const int Kw = slabs * (RB / 4), nch = (m.exp + 31) / 32, Np = nch * 32, KK = m.k * m.k;
+                const size_t owe = B.alloc(sizeof(float) * 2 * (size_t)Np * Kw), ope = B.alloc(sizeof(float) * (size_t)nch * (2 + KK) * 32);
+                memset(B.f(owe), 0, sizeof(float) * 2 * (size_t)Np * Kw);
+                memset(B.f(ope), 0, sizeof(float) * (size_t)nch * (2 + KK) * 32);
+                for (int n = 0; n < m.exp; n++)
+                    for (int k = 0; k < m.cin; k++) {
+                        const float wv = B.f(o_wexp)[(size_t)k * m.exp + n];
+                        const float hi = to_tf32(wv);
+                        B.f(owe)[(size_t)n * Kw + k] = hi;
+                        B.f(owe)[((size_t)Np + n) * Kw + k] = to_tf32(wv - hi);
+                    }
+                for (int n = 0; n < m.exp; n++) {
+                    float* blk = B.f(ope) + (size_t)(n / 32) * (2 + KK) * 32;
+                    blk[n % 32] = B.f(o_bexp)[n];
+                    blk[32 + n % 32] = B.f(ob)[n];
+                    for (int t = 0; t < KK; t++) blk[(2 + t) * 32 + n % 32] = B.f(ow)[(size_t)t * m.exp + n];
+                }
+                reg(&m.wed_exp, owe); reg(&m.ed_params, ope);
+            }
         }
         if (m.se) {   // fc1 [sq][exp] -> [exp][sq]; fc2 [exp][sq] -> [sq][exp]
             const float* w1 = c.next(); const float* b1 = c.next(); const float* w2 = c.next(); const float* b2 = c.next();
