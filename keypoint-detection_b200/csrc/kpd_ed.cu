@@ -15,7 +15,7 @@
 //   compute warps : (16 warps) tcgen05.ld -> +bias, activation -> the chunk's expanded tile in shared memory
 //                   [image][row + halo][col + halo][32 ch + 4 pad], zero where the depthwise conv pads -> depthwise conv with a
 //                   lane per channel and a k-row register window (the inner loop of kpd_dw.cu) -> coalesced 128-byte stores of
-//                   the block's depthwise output, per-(image, band) squeeze partials in a fixed order (deterministic)
+//                   the block's depthwise output, per-(image, output row) squeeze partials in a canonical order
 // While the compute warps work on chunk c the tensor core already holds chunk c+1 and the TMA ring chunk c+2..3; the next
 // item's pixels land during the current item.  Only the depthwise output (what the SE excitation and the projection need)
 // goes back to memory.
@@ -43,7 +43,7 @@ constexpr int ED_THREADS = 192 + ED_CTHREADS;                 // 22 warps: TMA, 
 constexpr int ED_MAXT = 8, ED_MAXG = 8, ED_MAXBST = 4;
 
 struct EdParams {
-    float* out; float* pool;         // depthwise output [B][Ho][Wo][C]; squeeze partials [B][bands][C] (may be null)
+    float* out; float* pool;         // depthwise output [B][Ho][Wo][C]; squeeze partials [B][Ho][C], one per output row (may be null)
     const float* params;             // [nchunks][2 + k*k][32]: expand bias | depthwise bias | tap rows
     int B, H, W, Ho, Wo, C, K, act;
     int G, TH, bands, total_items, nchunks;
@@ -87,7 +87,7 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     uint8_t* sA = smem;                                     // [3 parts][slabs][P8 rows][RB]: parts 0 / 1 = raw -> hi ring, part 2 = lo
     uint8_t* sB = smem + p.off_b;                           // [bstages][hi rows | lo rows | params]
     float* sE = reinterpret_cast<float*>(smem + p.off_e);   // [nbuf][G][in_h][Wp][ED_ES]
-    float* red = reinterpret_cast<float*>(smem + p.off_red);   // [2 chunk parities][G][compute warps][32] squeeze partials
+    float* rowp = reinterpret_cast<float*>(smem + p.off_red);  // [G][TH][runs][32] squeeze partials of the current chunk, one per (output row, run)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
     const int BST = p.bstages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * ED_MAXBST);
@@ -265,22 +265,24 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         {   // the tile starts as zeros: halo columns and the rows above / below a whole image are never written again
             const int total = p.nbuf * p.ebuf_floats;
             for (int i = ctid * 4; i < total; i += ED_CTHREADS * 4) *reinterpret_cast<float4*>(sE + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = ctid; i < 2 * p.G * ED_CWARPS * 32; i += ED_CTHREADS) red[i] = 0.f;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(ED_CTHREADS) : "memory");
         uint32_t q = 0;
         int bs = 0; uint32_t bph = 0;
-        // squeeze partials of the chunk that ran under `q_done` -> pool[(image, band)][channel], slots added in warp order
-        auto finish_pool = [&](uint32_t q_done, int c_done, const Item& it) {
+        // Squeeze partials in a CANONICAL order, so that an image's SE excitation does not depend on how this launch was cut into
+        // bands / image groups / work units (the trunk stays bit-identical across batch sizes): a thread stores the sum of its
+        // XR outputs of ONE output row; here the runs of a row are added left to right and the row total goes to
+        // pool[image][output row][channel]; the SE kernel adds the rows top to bottom.
+        auto finish_pool = [&](int c_done, const Item& it, int runs) {
             if (!p.pool) return;
-            float* rb = red + (q_done & 1u) * (p.G * ED_CWARPS * 32);
-            for (int i = ctid; i < it.gcnt * 32; i += ED_CTHREADS) {
-                const int g = i >> 5, ch = i & 31;
+            const int per_g = it.th * 32;
+            for (int i = ctid; i < it.gcnt * per_g; i += ED_CTHREADS) {
+                const int g = i / per_g, rem = i - g * per_g, y = rem >> 5, ch = rem & 31;
                 if (c_done * ED_CW + ch < p.C) {
+                    const float* rp = rowp + ((g * p.TH + y) * runs) * 32 + ch;
                     float tot = 0.f;
-#pragma unroll
-                    for (int w = 0; w < ED_CWARPS; w++) tot += rb[(g * ED_CWARPS + w) * 32 + ch];
-                    p.pool[((size_t)(it.b0 + g) * p.bands + it.band) * p.C + c_done * ED_CW + ch] = tot;
+                    for (int r = 0; r < runs; r++) tot += rp[r * 32];
+                    p.pool[((size_t)(it.b0 + g) * p.Ho + it.oy0 + y) * p.C + c_done * ED_CW + ch] = tot;
                 }
             }
         };
@@ -363,13 +365,10 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty(a));
                 if (cw == 0 && lane == 0) ED_TRACE(0, tev + 3);
-                asm volatile("bar.sync 1, %0;" ::"n"(ED_CTHREADS) : "memory");        // the chunk's tile is complete (and the previous chunk's squeeze partials)
+                asm volatile("bar.sync 1, %0;" ::"n"(ED_CTHREADS) : "memory");        // the chunk's tile is complete
                 if (cw == 0 && lane == 0) ED_TRACE(0, tev + 4);
-                if (c > 0) finish_pool(q - 1, c - 1, it);
                 // ---- depthwise conv on the tile: lane = channel, warp = (image, row segment, run of XR columns) work units
                 const bool active = c * ED_CW + lane < p.C;
-                float* rb = red + (q & 1u) * (p.G * ED_CWARPS * 32);
-                for (int g = 0; g < it.gcnt; g++) rb[(g * ED_CWARPS + cw) * 32 + lane] = 0.f;   // own slots (read out two chunks ago)
                 for (int idx = cw; idx < nwork; idx += ED_CWARPS) {
                     const int g = idx / per_img, rem = idx - g * per_img, yseg = rem / runs, run = rem - yseg * runs;
                     const int y0 = yseg * p.YS, nrows = min(p.YS, it.th - y0);
@@ -378,7 +377,7 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     // (lanes past the last channel of a partial chunk run on zero weights with nvalid = 0: they store nothing)
                     float* op = p.out + (((size_t)(it.b0 + g) * p.Ho + it.oy0 + y0) * p.Wo + ox0) * p.C + c * ED_CW + lane;
                     const int opitch = p.Wo * p.C;
-                    float ssum = 0.f;
+                    float* rsum = rowp + ((g * p.TH + y0) * runs + run) * 32 + lane;      // this unit's (row, run) squeeze partials
                     // rolling window of KS input rows in registers (slot = input row mod KS, segment-relative): one output row costs
                     // S * SEG shared-memory loads against XR * k*k FMAs; the other three warps of the sub-partition cover the latency
                     float win[KS][SEG];
@@ -411,24 +410,24 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                                 for (int j = 0; j < XR; j++) asm volatile("" : "+f"(acc[j]));
                                 float* orow = op + (size_t)i * opitch;
+                                float rs = 0.f;
 #pragma unroll
                                 for (int j = 0; j < XR; j++) {
                                     const float x = acc[j];
                                     // hardswish x * relu6(x + 3) / 6 as x * sat(x / 6 + 0.5): one FFMA.SAT + one FMUL
                                     const float v = hsw ? x * __saturatef(fmaf(x, 1.f / 6.f, 0.5f)) : fmaxf(x, 0.f);
-                                    if (j < nvalid) { orow[j * p.C] = v; ssum += v; }
+                                    if (j < nvalid) { orow[j * p.C] = v; rs += v; }
                                 }
+                                rsum[i * runs * 32] = rs;
                             }
                         }
                     }
-                    rb[(g * ED_CWARPS + cw) * 32 + lane] += ssum;      // slot owned by this thread: plain read-modify-write
                 }
                 if (cw == 0 && lane == 0) ED_TRACE(0, tev + 5);
-                if (p.nbuf == 1) asm volatile("bar.sync 1, %0;" ::"n"(ED_CTHREADS) : "memory");   // single tile buffer: reads done before the next chunk overwrites it
+                // every warp is done with the tile (a single tile buffer may now be overwritten) and the row partials are complete
+                asm volatile("bar.sync 1, %0;" ::"n"(ED_CTHREADS) : "memory");
+                finish_pool(c, it, runs);
             }
-            // the item's last chunk: publish its squeeze partials (its slots are rewritten only two barriers from now)
-            asm volatile("bar.sync 1, %0;" ::"n"(ED_CTHREADS) : "memory");
-            finish_pool(q - 1, p.nchunks - 1, it);
         }
     }
     tc_fence_before();
@@ -479,7 +478,8 @@ static bool ed_layout(EdParams& p, int KS, int S, int G, int TH, int nbuf, int b
     p.off_e = p.off_b + bstages * p.bstage_bytes;
     const int slack = 8 * ED_ES * 4 + 64;                    // a partial last run reads a few pixels past its row
     p.off_red = (p.off_e + nbuf * p.ebuf_floats * 4 + slack + 15) & ~15;
-    p.off_bar = (p.off_red + 2 * G * ED_CWARPS * 32 * 4 + 15) & ~15;
+    const int runs = (p.Wo + ed_xr(KS, S) - 1) / ed_xr(KS, S);
+    p.off_bar = (p.off_red + G * std::min(TH, p.Ho) * runs * 32 * 4 + 15) & ~15;
     int cols = 32; while (cols < 2 * p.T * ED_CW) cols <<= 1;
     p.tmem_cols = cols;
     return cols <= 512 && ed_smem_bytes(p) <= 227 * 1024;
@@ -565,8 +565,8 @@ int expand_depthwise_fused(const MBBlock& m, const float* in, float* out, float*
     }
     if (!cfg.ok || !ed_layout(p, KS, S, cfg.G, cfg.TH, cfg.nbuf, cfg.bstages)) return KPD_ERR_UNSUPPORTED;
     p.YS = cfg.YS;
-    if (pool_parts) *pool_parts = p.bands;
-    if (pool && (size_t)p.bands * m.exp > pool_capacity) { set_error("expand_depthwise_fused: SE partial buffer too small"); return KPD_ERR_STATE; }
+    if (pool_parts) *pool_parts = p.Ho;                      // one squeeze partial per output row (canonical summation order)
+    if (pool && (size_t)p.Ho * m.exp > pool_capacity) { set_error("expand_depthwise_fused: SE partial buffer too small"); return KPD_ERR_STATE; }
     const int64_t items = (int64_t)((B + p.G - 1) / p.G) * p.bands;
     if (items >= ((int64_t)1 << 31)) return KPD_ERR_UNSUPPORTED;
     p.total_items = (int)items;

@@ -85,6 +85,7 @@ class MultiPersonKeypointModel(nn.Module):
         self._chunk_streams, self._chunk_workspaces = [], []     # host-input pipelining (forward)
         self._tensors = None
         self._last = None
+        self._pipe = None                                        # submit(): copy stream + two device input slots
 
     # ------------------------------------------------------------------ plumbing
     def set_precision(self, precision: str):
@@ -218,6 +219,53 @@ class MultiPersonKeypointModel(nn.Module):
             self.eval()
         return self.forward(batch, **kw)
 
+    # ------------------------------------------------------------------ pipelined host-input path
+    def submit(self, batch):
+        """Asynchronous predict for HOST-resident batches (pinned memory recommended): enqueue the H2D copy of this batch on
+        a copy stream and its forward on the current stream, and return a PendingResult immediately.  The copy of batch i+1
+        overlaps the kernels of batch i (two input slots), which is what a DataLoader-fed inference loop wants:
+
+            pending = model.submit(next(it))
+            for nxt in it:
+                upcoming = model.submit(nxt)        # its H2D runs under the current batch's kernels
+                out = pending.result()              # dict as returned by predict(); device tensors, forward finished
+                pending = upcoming
+
+        Same results as predict() bit for bit (the same kpd_forward call on the same device tensors)."""
+        if self.training:
+            self.eval()
+        x = batch['image'] if isinstance(batch, dict) else batch
+        boxes = batch.get('bboxes') if isinstance(batch, dict) else None
+        if not isinstance(x, torch.Tensor) or not isinstance(boxes, torch.Tensor) or boxes.dim() != 3 or x.device.type != "cpu":
+            # anything but the plain (host image tensor, host [B,P,4] boxes) form: no pipelining, run it now
+            return PendingResult(self.predict(batch), None)
+        plan, dev = self._plan()
+        with torch.cuda.device(dev):
+            pipe = self._pipe
+            if pipe is None:
+                pipe = self._pipe = {"copy": torch.cuda.Stream(device=dev), "slot": 0, "x": [None, None], "b": [None, None],
+                                     "free": [None, None]}
+            slot = pipe["slot"]; pipe["slot"] = slot ^ 1
+            cur = torch.cuda.current_stream(dev)
+            xs, bs = pipe["x"][slot], pipe["b"][slot]
+            if xs is None or xs.shape != x.shape:
+                xs = pipe["x"][slot] = torch.empty(x.shape, dtype=torch.float32, device=dev)
+            if bs is None or bs.shape != boxes.shape:
+                bs = pipe["b"][slot] = torch.empty(boxes.shape, dtype=torch.float32, device=dev)
+            with torch.cuda.stream(pipe["copy"]):
+                if pipe["free"][slot] is not None:
+                    pipe["copy"].wait_event(pipe["free"][slot])          # the forward that last read this slot has finished
+                xs.copy_(x, non_blocking=True)
+                bs.copy_(boxes, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(pipe["copy"])
+            cur.wait_event(copied)
+            out = self.forward({'image': xs, 'bboxes': bs})
+            done = torch.cuda.Event()
+            done.record(cur)
+            pipe["free"][slot] = done
+        return PendingResult(out, done)
+
     def stage_tensors(self):
         """Views (NHWC) of the intermediate tensors of the last forward, for stage-wise parity tests."""
         if self._last is None:
@@ -264,6 +312,23 @@ class MultiPersonKeypointModel(nn.Module):
                                                    N.stream_ptr(dev)), "kpd_roi_align")
                     outs.append(o[..., :min(64, cs - h0)].permute(0, 3, 1, 2))
         return torch.cat(outs, dim=1)
+
+
+class PendingResult:
+    """Handle returned by MultiPersonKeypointModel.submit(): result() waits for the forward and returns its output dict."""
+
+    def __init__(self, out, event):
+        self._out, self._event = out, event
+
+    def result(self):
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = None
+        return self._out
+
+    def outputs(self):
+        """The (possibly still in-flight) output dict: enqueue further work on the same stream without waiting."""
+        return self._out
 
 
 def select_top_k_channels(features, channel_attention, k=64):

@@ -571,6 +571,13 @@ def test_bench_config_c2_against_oracle(style, mode, tol):
     host = m.predict({"image": x.pin_memory(), "bboxes": boxes.pin_memory()})            # chunked H2D path (images 128..255 = chunk 2)
     assert torch.equal(free["heatmap"], host["heatmap"]) and torch.equal(free["keypoints"], host["keypoints"])
     assert torch.equal(free["visibilities"], host["visibilities"])
+    # pipelined submit(): three batches in flight over the two input slots, each equal to the blocking call
+    xp, bp = x.pin_memory(), boxes.pin_memory()
+    x2 = torch.flip(x, dims=[0]).contiguous().pin_memory()
+    pend = [m.submit({"image": xp, "bboxes": bp}), m.submit({"image": x2, "bboxes": bp}), m.submit({"image": xp, "bboxes": bp})]
+    res = [p.result() for p in pend]
+    assert torch.equal(res[0]["heatmap"], free["heatmap"]) and torch.equal(res[2]["keypoints"], free["keypoints"])
+    assert torch.equal(res[1]["heatmap"], torch.flip(free["heatmap"], dims=[0]))     # reversed batch: per-image results, reversed
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-2), ("bf16", 1e-1)])
