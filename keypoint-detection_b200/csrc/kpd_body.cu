@@ -9,8 +9,6 @@
 
 namespace kpd {
 
-int run_mbconv(const kpd_plan* p, const MBBlock& m, const float* in, float* out, int B, int H, int strict_fp32, cudaStream_t s);
-
 int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts, int B, int H, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
@@ -163,52 +161,6 @@ int pointwise(const float* in, const float* w, const float* bias, float* out, in
     return launch_pw(a, s);
 }
 
-// ------------------------------------------------------------------------------------------------
-// depthwise k x k (stride 1|2, pad (k-1)/2) + folded BN + act, NHWC; optional SE squeeze (sum over H*W per (b,c)).
-// thread = (output pixel, 4 channels).  blockDim = (C/4 rounded to a divisor layout) handled by flat indexing.
-template <int K>
-__global__ void __launch_bounds__(256) dw_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                 const float* __restrict__ bias, float* __restrict__ out,
-                                                 float* __restrict__ pool, int B, int H, int C, int stride, int act) {
-    const int Ho = H / stride, C4 = C >> 2, pad = (K - 1) / 2;
-    const int64_t per_img = (int64_t)Ho * Ho * C4;
-    const int b = blockIdx.y;
-    extern __shared__ float red[];                       // [C] per-block SE partial sums
-    if (pool) { for (int i = threadIdx.x; i < C; i += blockDim.x) red[i] = 0.f; __syncthreads(); }
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(t % C4); const int64_t pix = t / C4;
-        const int ox = (int)(pix % Ho), oy = (int)(pix / Ho);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int ky = 0; ky < K; ky++) {
-            const int iy = oy * stride - pad + ky;
-            if (iy < 0 || iy >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < K; kx++) {
-                const int ix = ox * stride - pad + kx;
-                if (ix < 0 || ix >= H) continue;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(in + (((int64_t)b * H + iy) * H + ix) * C) + c4);
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (ky * K + kx) * C) + c4);
-                acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-                acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
-            }
-        }
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-        float4 r;
-        r.x = apply_act(acc.x + bb.x, act); r.y = apply_act(acc.y + bb.y, act);
-        r.z = apply_act(acc.z + bb.z, act); r.w = apply_act(acc.w + bb.w, act);
-        reinterpret_cast<float4*>(out + (((int64_t)b * Ho + oy) * Ho + ox) * C)[c4] = r;
-        if (pool) {
-            atomicAdd(&red[c4 * 4 + 0], r.x); atomicAdd(&red[c4 * 4 + 1], r.y);
-            atomicAdd(&red[c4 * 4 + 2], r.z); atomicAdd(&red[c4 * 4 + 3], r.w);
-        }
-    }
-    if (pool) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(pool + (int64_t)b * C + i, red[i]);
-    }
-}
-
 // SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 ).
 // One CTA per SE_IMG images (the weight matrices are read once per CTA, not once per image: at C = 576 they are 2 x 332 KB).
 // A layer is spread over (4-output group, k-slice) threads with the S slices of a group in ADJACENT lanes: every thread
@@ -297,22 +249,10 @@ static int launch_se_fc(const MBBlock& m, const float* pool, int parts, float* s
     return 0;
 }
 
-static int launch_dw(const MBBlock& m, const float* in, float* out, float* pool, int B, int H, cudaStream_t s) {
-    const int Ho = H / m.stride;
-    const int64_t per_img = (int64_t)Ho * Ho * (m.exp / 4);
-    int gx = (int)std::min<int64_t>((per_img + 255) / 256, 64);
-    dim3 grid(gx, B);
-    const size_t sm = pool ? sizeof(float) * m.exp : 0;
-    if (m.k == 3) dw_kernel<3><<<grid, 256, sm, s>>>(in, m.w_dw, m.b_dw, out, pool, B, H, m.exp, m.stride, m.act);
-    else          dw_kernel<5><<<grid, 256, sm, s>>>(in, m.w_dw, m.b_dw, out, pool, B, H, m.exp, m.stride, m.act);
-    KPD_LAUNCH_CHECK();
-    return 0;
-}
-
-// Batch-wide trunk: every 1x1 conv is one fp32 GEMM over all B*H*W pixels (CUDA-core FFMA, kpd_pwf.cu; KPD_PW_MMA=1
-// selects the 3xTF32 mma.sync predecessor), every depthwise conv one batch-wide TMA-staged kernel (kpd_dw.cu).  At the batch sizes of the benchmark configs the per-image problems (<= 56x56 pixels)
-// are too small to fill an SM, so the batch-wide form beats the one-cluster-per-image fused kernel (kpd_mbconv.cu);
-// the intermediates (expanded / depthwise tensors) stay L2-resident for B*H*W*C*4 B <= ~100 MB.
+// Batch-wide trunk.  Per inverted-residual block: [expand 1x1 + depthwise k x k + squeeze partials] as ONE kernel with the
+// expanded tensor on chip (kpd_ed.cu; fp32 / bf16 modes), the SE excitation MLP, and the projection GEMM with the excitation
+// applied to its A operand and the residual added in its epilogue (tcgen05 3xTF32, kpd_pwu.cu, or exact CUDA-core fp32,
+// kpd_pwf.cu).  Strict mode and bands that do not fit an SM take the separate expand GEMM + TMA-staged depthwise (kpd_dw.cu).
 static int run_body_batched(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     char* scratch = ws + L.scratch;
     const ScratchMap sm = scratch_map(B, S, 1);
@@ -351,9 +291,9 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
         }
         if (!fused) {
             if (m.w_exp) {
-                PwMma a{}; a.A = cur; a.Wf = m.wf_exp; a.Wraw = m.w_exp; a.Wu = m.wu_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act; a.exact = strict_fp32;
+                PwMma a{}; a.A = cur; a.Wraw = m.w_exp; a.Wu = m.wu_exp; a.bias = m.b_exp; a.out = expand; a.M = (int64_t)B * H * H; a.K = m.cin; a.N = m.exp; a.act = m.act; a.exact = strict_fp32;
                 ProfScope ps("body.pointwise", s);
-                KPD_TRY(pointwise_mma(a, p->sm_count, s));
+                KPD_TRY(pointwise_gemm(a, p->sm_count, s));
                 x = expand;
             }
             ProfScope ps("body.depthwise", s);
@@ -364,71 +304,19 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
             KPD_TRY(launch_se_fc(m, se_pool, pool_parts, se_scale, B, 1.f / (float)(Ho * Ho), s));
         }
         float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
-        PwMma a{}; a.A = dwout; a.Wf = m.wf_proj; a.Wraw = m.w_proj; a.Wu = m.wu_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE; a.exact = strict_fp32;
+        PwMma a{}; a.A = dwout; a.Wraw = m.w_proj; a.Wu = m.wu_proj; a.bias = m.b_proj; a.out = dst; a.M = (int64_t)B * Ho * Ho; a.K = m.exp; a.N = m.cout; a.act = ACT_NONE; a.exact = strict_fp32;
         a.se_scale = m.se ? se_scale : nullptr; a.hw = Ho * Ho; a.res = m.res ? cur : nullptr; a.res_mode = m.res ? 1 : 0;
-        { ProfScope ps("body.pointwise", s); KPD_TRY(pointwise_mma(a, p->sm_count, s)); }
+        { ProfScope ps("body.pointwise", s); KPD_TRY(pointwise_gemm(a, p->sm_count, s)); }
         cur = dst; H = Ho;
     }
-    PwMma a{}; a.A = cur; a.Wf = p->wf_last; a.Wraw = p->w_last; a.Wu = p->wu_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH; a.exact = strict_fp32;
+    PwMma a{}; a.A = cur; a.Wraw = p->w_last; a.Wu = p->wu_last; a.bias = p->b_last; a.out = feat[3]; a.M = (int64_t)B * H * H; a.K = 96; a.N = 576; a.act = ACT_HSWISH; a.exact = strict_fp32;
     ProfScope ps("body.pointwise", s);
-    return pointwise_mma(a, p->sm_count, s);
+    return pointwise_gemm(a, p->sm_count, s);
 }
 
 int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
-    static const bool fused = getenv("KPD_BODY_FUSED") != nullptr;           // one-cluster-per-image fused MBConv kernels
-    // default in every precision mode: the batch-wide pipeline is exact fp32 on CUDA cores (FFMA GEMMs, FMA depthwise)
-    if (!fused && getenv("KPD_BODY_UNFUSED") == nullptr) { ProfScope ps("body", s); return run_body_batched(p, images, B, S, strict_fp32, want_f0_tf32, ws, L, s); }
     ProfScope ps("body", s);
-    char* scratch = ws + L.scratch;
-    const ScratchMap sm = scratch_map(B, S, 1);
-    float* f0_tf32 = want_f0_tf32 ? reinterpret_cast<float*>(scratch + sm.f0_tf32) : nullptr;
-    float* feat[4]; for (int i = 0; i < 4; i++) feat[i] = reinterpret_cast<float*>(ws + L.feat[i]);
-    float* expand = reinterpret_cast<float*>(scratch + sm.expand);
-    float* dwout = reinterpret_cast<float*>(scratch + sm.dwout);
-    float* ping = reinterpret_cast<float*>(scratch + sm.ping);
-    float* pong = reinterpret_cast<float*>(scratch + sm.pong);
-    float* se_pool = reinterpret_cast<float*>(scratch + sm.se_pool);
-    float* se_scale = reinterpret_cast<float*>(scratch + sm.se_scale);
-
-    {
-        const int64_t total = (int64_t)B * (S / 2) * (S / 2) * 4;
-        int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)p->sm_count * 16);
-        stem_kernel<<<grid, 256, 0, s>>>(images, p->w_stem, p->b_stem, feat[0], f0_tf32, B, p->in_channels, S);
-        KPD_LAUNCH_CHECK();
-    }
-    const float* cur = feat[0];
-    int H = S / 2;
-    static const bool unfused = getenv("KPD_BODY_UNFUSED") != nullptr;     // debugging aid: layer-by-layer kernels
-    for (int i = 0; i < 11; i++) {
-        const MBBlock& m = p->blocks[i];
-        const int Ho = H / m.stride;
-        if (!unfused) {
-            float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
-            const int r = run_mbconv(p, m, cur, dst, B, H, strict_fp32, s);
-            if (r == 0) { cur = dst; H = Ho; continue; }
-            if (r != KPD_ERR_UNSUPPORTED) return r;                         // does not fit on chip (large S): layer-by-layer
-        }
-        const float* x = cur;
-        if (m.w_exp) {
-            KPD_TRY(pointwise(cur, m.w_exp, m.b_exp, expand, (int64_t)B * H * H, m.cin, m.exp, m.act, nullptr, nullptr, 0, s));
-            x = expand;
-        }
-        float* pool = nullptr;
-        if (m.se) { KPD_CUDA(cudaMemsetAsync(se_pool, 0, sizeof(float) * B * m.exp, s)); pool = se_pool; }
-        KPD_TRY(launch_dw(m, x, dwout, pool, B, H, s));
-        const float* scale = nullptr;
-        if (m.se) {
-            KPD_TRY(launch_se_fc(m, se_pool, 1, se_scale, B, 1.f / (float)(Ho * Ho), s));
-            scale = se_scale;
-        }
-        // block outputs that the FPN consumes are written straight into their feat slot (features.3 / features.8)
-        float* dst = (i == 2) ? feat[1] : (i == 7) ? feat[2] : (cur == ping ? pong : ping);
-        KPD_TRY(pointwise(dwout, m.w_proj, m.b_proj, dst, (int64_t)B * Ho * Ho, m.exp, m.cout, ACT_NONE,
-                          m.res ? cur : nullptr, scale, Ho * Ho, s));
-        cur = dst; H = Ho;
-    }
-    KPD_TRY(pointwise(cur, p->w_last, p->b_last, feat[3], (int64_t)B * H * H, 96, 576, ACT_HSWISH, nullptr, nullptr, 0, s));
-    return 0;
+    return run_body_batched(p, images, B, S, strict_fp32, want_f0_tf32, ws, L, s);
 }
 
 // lateral_convs[0] (1x1, 16 -> 128, no bias) + nearest x`up` upsample-add of the coarser lateral: a pure streaming
@@ -569,11 +457,11 @@ int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict
     if ((int64_t)B * hs[0] * hs[0] >= (int64_t)1 << 31) { set_error("fpn laterals: B*H*W = %lld pixels exceeds the 32-bit pixel index", (long long)B * hs[0] * hs[0]); return KPD_ERR_UNSUPPORTED; }
     (void)strict_fp32;                                  // every lateral is exact fp32 on CUDA cores; the modes differ only in round_tf32
     for (int i = 3; i >= 1; i--) {                       // laterals 3..1: fp32 GEMM + nearest-upsample add in the epilogue
-        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wf = p->wf_lat[i]; a.Wraw = p->w_lat[i]; a.Wu = p->wu_lat[i]; a.out = lat[i];
+        PwMma a{}; a.A = reinterpret_cast<const float*>(ws + L.feat[i]); a.Wraw = p->w_lat[i]; a.Wu = p->wu_lat[i]; a.out = lat[i];
         a.M = (int64_t)B * hs[i] * hs[i]; a.K = cin[i]; a.N = 128; a.act = ACT_NONE; a.hw = hs[i] * hs[i]; a.exact = strict_fp32;
         if (i < 3) { a.res = lat[i + 1]; a.res_mode = 2; a.H = hs[i]; a.W = hs[i]; a.up = hs[i] / hs[i + 1]; }
         a.round_tf32 = (composed && i == 1) ? 1 : 0;
-        KPD_TRY(pointwise_mma(a, p->sm_count, s));
+        KPD_TRY(pointwise_gemm(a, p->sm_count, s));
     }
     if (composed) return 0;
     // strict mode only: lateral 0 (1x1, 16 -> 128) + x4 nearest top-down add, materialised by a CUDA-core streaming kernel

@@ -75,9 +75,6 @@ struct MBBlock {
     const float *w_fc1, *b_fc1;     // SE fc1                          [exp][sq], [sq]
     const float *w_fc2, *b_fc2;     // SE fc2                          [sq][exp], [exp]
     const float *w_proj, *b_proj;   // project 1x1 (+folded BN)       [exp][cout], [cout]
-    // the same 1x1 weights pre-split for 3xTF32 mma.sync (m16n8k8 B fragments): float4 [K/8][N/8][32 lanes] =
-    // (b0_hi, b1_hi, b0_lo, b1_lo), b0 = W[k0+t][n0+g], b1 = W[k0+t+4][n0+g], g = lane>>2, t = lane&3
-    const float4 *wf_exp, *wf_proj;
     // fused expand + depthwise kernel (kpd_ed.cu): expand weights as tf32 hi / lo rows [2][ceil(exp/32)*32][slabs * row floats]
     // (K-major, zero padded) and per 32-channel chunk one block [2 + k*k][32] = expand bias | depthwise bias | tap rows
     const float *wed_exp, *ed_params;
@@ -104,10 +101,8 @@ struct kpd_plan {
     kpd::MBBlock blocks[11];
     const float *w_last, *b_last;                 // f12 [96][576], [576]
     const float* wu_last; const float* wu_lat[4];  // tf32 hi / lo splits for the tcgen05 pointwise GEMM
-    const float4* wf_last;                        // f12 as 3xTF32 mma fragments
     // fpn
     const float* w_lat[4];                        // [cin_i][128]
-    const float4* wf_lat[4];                      // laterals as 3xTF32 mma fragments
     kpd::DenseConv lat0_conv;                     // lateral 0 (1x1, 16 -> 128) packed for the tcgen05 kernel (64-byte K rows)
     // FPN-0 in composed form (kpd_fpn0.cu): conv3x3(L0 f0 + up4(lat1)) = conv3x3_{W1}(f0) + sum over coarse neighbours W2 lat1
     const float* fpn0c_w1;                        // [128 cout][9 taps * 16 cin] tf32: fpn_convs[0] (BN folded) composed with lateral_convs[0]
@@ -151,7 +146,7 @@ int pointwise(const float* in, const float* w, const float* bias, float* out, in
               int act, const float* residual, const float* se_scale, int hw_per_image, cudaStream_t s);
 // Batch-wide pointwise (1x1) convolution as a GEMM over all pixels: out[M][N] = act(A[M][K] * W[K][N] + bias) (+ residual).
 struct PwMma {
-    const float* A; const float4* Wf; const float* bias; float* out;   // Wf: 3xTF32 mma.sync B fragments (kpd_pw.cu)
+    const float* A; const float* bias; float* out;
     int64_t M; int K, N, act;
     const float* se_scale; int hw;           // optional [image][K] scale applied to A (SE excitation), hw = pixels/image
     const float* res; int res_mode;          // 0 none, 1 same-shape add, 2 nearest-upsampled add (FPN top-down)
@@ -167,7 +162,7 @@ void ed_operand_shape(int K, int* RB, int* slabs);
 int expand_depthwise_fused(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts,
                            int B, int H, int sm_count, cudaStream_t s);
 void pwu_chunks(int N, int* nchunks, int* Nc);
-int pointwise_mma(const PwMma& p, int sm_count, cudaStream_t s);
+int pointwise_gemm(const PwMma& p, int sm_count, cudaStream_t s);      // dispatch: tcgen05 3xTF32 / CUDA-core fp32 (kpd_pw.cu)
 int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s);
 
 }  // namespace kpd

@@ -125,23 +125,6 @@ static void pack_dense(Blob& B, const float* w, const float* cbias, const BN* bn
     }
 }
 
-// 3xTF32 B-fragment packing of a [K][N] matrix already stored in the blob at `off_w` (see MBBlock::wf_exp)
-static size_t pack_mma_frag(Blob& B, size_t off_w, int K, int N) {
-    const int k8 = K / 8, n8 = N / 8;
-    size_t off = B.alloc(sizeof(float) * 4 * (size_t)k8 * n8 * 32);
-    for (int kb = 0; kb < k8; kb++)
-        for (int nb = 0; nb < n8; nb++)
-            for (int lane = 0; lane < 32; lane++) {
-                const int g = lane >> 2, t = lane & 3;
-                const float b0 = B.f(off_w)[(size_t)(kb * 8 + t) * N + nb * 8 + g];
-                const float b1 = B.f(off_w)[(size_t)(kb * 8 + t + 4) * N + nb * 8 + g];
-                const float h0 = to_tf32(b0), h1 = to_tf32(b1);
-                float* d = B.f(off) + (((size_t)kb * n8 + nb) * 32 + lane) * 4;
-                d[0] = h0; d[1] = h1; d[2] = to_tf32(b0 - h0); d[3] = to_tf32(b1 - h1);
-            }
-    return off;
-}
-
 // tf32 hi / lo split of a [K][N] matrix stored in the blob at `off_w`, as K-major rows [2][Np][Kp] (kpd_pwu.cu)
 static size_t pack_umma_split(Blob& B, size_t off_w, int K, int N) {
     int nchunks, Nc; kpd::pwu_chunks(N, &nchunks, &Nc);
@@ -246,7 +229,6 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.exp, m.cin, 1, ow, ob);
             o_wexp = ow; o_bexp = ob;
             reg(&m.w_exp, ow); reg(&m.b_exp, ob);
-            reg(&m.wf_exp, pack_mma_frag(B, ow, m.cin, m.exp));
             reg(&m.wu_exp, pack_umma_split(B, ow, m.cin, m.exp));
         }
         {   // depthwise [exp][1][k][k] -> [k*k][exp]
@@ -289,7 +271,6 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
             const float* w = c.next(); BN bn = read_bn(c);
             pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, m.cout, m.exp, 1, ow, ob);
             reg(&m.w_proj, ow); reg(&m.b_proj, ob);
-            reg(&m.wf_proj, pack_mma_frag(B, ow, m.exp, m.cout));
             reg(&m.wu_proj, pack_umma_split(B, ow, m.exp, m.cout));
         }
     }
@@ -297,7 +278,6 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         const float* w = c.next(); BN bn = read_bn(c);
         pack_conv_kc(B, w, nullptr, &bn, EPS_BODY, 576, 96, 1, ow, ob);
         reg(&p->w_last, ow); reg(&p->b_last, ob);
-        reg(&p->wf_last, pack_mma_frag(B, ow, 96, 576));
         reg(&p->wu_last, pack_umma_split(B, ow, 96, 576));
     }
     const int fpn_in[4] = {16, 24, 48, 576};
@@ -307,7 +287,6 @@ extern "C" int kpd_plan_create(kpd_plan** out, const kpd_model_desc* desc, const
         if (i == 0) w_lat0_raw = w;
         pack_conv_kc(B, w, nullptr, nullptr, 0, 128, fpn_in[i], 1, ow, ob);
         reg(&p->w_lat[i], ow);
-        reg(&p->wf_lat[i], pack_mma_frag(B, ow, fpn_in[i], 128));
         reg(&p->wu_lat[i], pack_umma_split(B, ow, fpn_in[i], 128));
     }
     auto dense = [&](DenseConv& d, const float* w, const float* cb, const BN* bn, double eps, int cout, int cin, int k) {
