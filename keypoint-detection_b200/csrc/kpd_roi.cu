@@ -11,13 +11,6 @@ namespace kpd {
 // feature-map element -> float (the map is fp32, or bf16 in bf16 mode)
 __device__ __forceinline__ float ld_feat(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_feat(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
-// four consecutive channels (16- / 8-byte aligned) -> float4
-__device__ __forceinline__ float4 ld_feat4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float4 ld_feat4(const __nv_bfloat16* p) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Order-preserving compaction of the non-zero boxes.  One block; images are walked in chunks of 1024 (thread = image) with a
@@ -151,6 +144,9 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FT* __restrict__ f
 // S = 224) -- and keeps it in shared memory; the outer sum then runs over <= g+1 shared-memory columns per output pixel.
 // Results differ from the sample-by-sample order only by fp32 re-association.  Needs g <= RA_MAXG (S <= 784); larger
 // maps use roi_align_kernel.
+// (Measured alternative, not kept: reading the whole 128-channel pixel as one coalesced row per lane-quad and selecting the 64
+//  channels in shared memory -- the 64 selected channels touch every 32-byte sector of a pixel anyway -- doubled the FMAs and
+//  turned phase 2 into a conflicted shared-memory gather: 0.65 ms against 0.33 ms for this lane-per-channel gather at C2.)
 constexpr int RA_MAXG = 7, RA_TAPS = RA_MAXG + 1;
 
 // Axis footprint of one output bin: first index touched, number of indices, and the accumulated weight of index first+j.
@@ -189,7 +185,7 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict
                                                             float* __restrict__ part, int H, int W) {
     const int n = blockIdx.y;
     if (roi_count && n >= *roi_count) return;
-    extern __shared__ __align__(16) float ra_v[];          // [span <= W][128]: column-wise partial interpolation of one output row, all channels
+    extern __shared__ __align__(16) float ra_v[];          // [span <= W][64]: column-wise partial interpolation of one output row
     __shared__ float wxs[56][RA_TAPS];
     __shared__ int xfirst[56], xcount[56];
     __shared__ float wys[2][RA_TAPS];
@@ -241,29 +237,26 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict
         float wy[NR];
 #pragma unroll
         for (int j = 0; j < NR; j++) wy[j] = wys[r][j];
-        // phase 1: one warp per feature column (CU columns in flight).  The 64 selected channels are spread over the pixel's 128
-        // (every 32-byte sector of the pixel holds some), so the WHOLE pixel is read as one coalesced row -- lane = 4 consecutive
-        // channels, one 16- / 8-byte load per lane per row -- and the selection happens in shared memory in phase 2.  (Gathering
-        // the selected channels lane by lane issued two scattered 2- / 4-byte requests per lane per row and was request-bound.)
-        constexpr int CU = 16 / NR;                        // 16 vector loads in flight per lane
+        // phase 1: one warp per feature column (CU columns in flight), lanes over the 64 selected channels
+        constexpr int CU = 16 / NR;                        // 32 gathers in flight per lane
         for (int cb = warp * CU; cb < ncol; cb += 8 * CU) {
-            float4 v[CU][NR];
+            float v0[CU][NR], v1[CU][NR];
 #pragma unroll
             for (int u = 0; u < CU; u++) {
-                const FT* px = fb + ((int64_t)yf * W + xs0 + min(cb + u, ncol - 1)) * 128 + 4 * lane;
+                const FT* px = fb + ((int64_t)yf * W + xs0 + min(cb + u, ncol - 1)) * 128;
 #pragma unroll
-                for (int j = 0; j < NR; j++) v[u][j] = j < nr ? ld_feat4(px + (int64_t)j * W * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < NR; j++) {
+                    if (j < nr) { v0[u][j] = ld_feat(px + (int64_t)j * W * 128 + c0); v1[u][j] = ld_feat(px + (int64_t)j * W * 128 + c1); }
+                    else { v0[u][j] = 0.f; v1[u][j] = 0.f; }
+                }
             }
 #pragma unroll
             for (int u = 0; u < CU; u++) {
                 if (cb + u >= ncol) break;
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                for (int j = 0; j < NR; j++) {
-                    a.x = fmaf(wy[j], v[u][j].x, a.x); a.y = fmaf(wy[j], v[u][j].y, a.y);
-                    a.z = fmaf(wy[j], v[u][j].z, a.z); a.w = fmaf(wy[j], v[u][j].w, a.w);
-                }
-                *reinterpret_cast<float4*>(ra_v + (cb + u) * 128 + 4 * lane) = a;
+                for (int j = 0; j < NR; j++) { a0 = fmaf(wy[j], v0[u][j], a0); a1 = fmaf(wy[j], v1[u][j], a1); }
+                ra_v[(cb + u) * 64 + lane] = a0; ra_v[(cb + u) * 64 + lane + 32] = a1;
             }
         }
         __syncthreads();
@@ -273,7 +266,7 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict
             float a0 = 0.f, a1 = 0.f;
             for (int j = 0; j < nc; j++) {
                 const float w = wxs[pw][j];
-                a0 = fmaf(w, ra_v[(xf + j) * 128 + c0], a0); a1 = fmaf(w, ra_v[(xf + j) * 128 + c1], a1);
+                a0 = fmaf(w, ra_v[(xf + j) * 64 + lane], a0); a1 = fmaf(w, ra_v[(xf + j) * 64 + lane + 32], a1);
             }
             a0 /= count; a1 /= count;
             float* o = roi_feat + (((int64_t)n * 56 + ph) * 56 + pw) * 64;
@@ -297,7 +290,7 @@ template <typename FT>
 static int launch_roi_align(const FT* fpn0, const int32_t* topk, const float* roi_box, const int32_t* roi_batch, const int32_t* roi_count,
                             float* roi_feat, float* part, int n, int H, int W, cudaStream_t s) {
     static const bool legacy = getenv("KPD_ROI_SAMPLEWISE") != nullptr;      // sample-by-sample form, kept for A/B checks
-    const size_t dyn = sizeof(float) * (size_t)W * 128;
+    const size_t dyn = sizeof(float) * (size_t)W * 64;
     const int gmax = std::max((H + 55) / 56, (W + 55) / 56);
     if (!legacy && gmax <= RA_MAXG && dyn <= 160 * 1024) {
         static uint64_t attr4 = 0, attr8 = 0;
