@@ -296,7 +296,7 @@ def roofline_other(kern, B, S, P, precision, pk, tf32_peak):
     n_roi = B * P
     bf16 = precision == "bf16"
     tpeak = tf32_peak or pk["burst"] / 2
-    fpn_elt = 2 if bf16 else 4
+    fpn_elt = 4                    # the FPN-0 map is fp32 in every mode
     out = {}
     if "fpn0_conv" in kern:
         ref_flops = 2.0 * B * (S // 2) ** 2 * 128 * 1152

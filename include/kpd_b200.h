@@ -61,7 +61,7 @@ typedef struct {
     int32_t batch, size, max_rois, precision;   /* what the layout was computed for */
     size_t feat[4];          /* fp32 [B,S/2,S/2,16] [B,S/8,S/8,24] [B,S/16,S/16,48] [B,S/32,S/32,576] */
     size_t lateral0;         /* fp32 [B,S/2,S/2,128] top-down sum feeding fpn_convs[0]; written only in strict-fp32 mode (the default modes fold it into the FPN-0 conv) */
-    size_t fpn0;             /* [B,S/2,S/2,128]: fp32, or bf16 in KPD_PREC_BF16 (the region is sized for fp32 either way) */
+    size_t fpn0;             /* fp32 [B,S/2,S/2,128]                                                  */
     size_t pool_avg;         /* fp32 [B,128]  */
     size_t pool_max;         /* fp32 [B,128]  */
     size_t scores;           /* fp32 [B,128]  */

@@ -15,7 +15,7 @@ struct DecodeArgs {
 int run_decode(const DecodeArgs& a, int dtype, int sm_count, cudaStream_t s);
 int run_dummy_person(const int32_t* img_count, float* vis, int B, int P, int K, cudaStream_t s);
 int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int run_roi_align(int B, int S, int n_max, const int32_t* topk, int feat_bf16, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
+int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int conv_dense_umma_halo(const kpd_plan* plan, const DenseConv& c, int prec_bf16, const void* in, void* out, int out_bf16,
                          int out_cm, int N, int H, int W, int act, int round_out_tf32, const int32_t* n_valid, cudaStream_t s);
@@ -166,8 +166,8 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     char* ws = static_cast<char*>(d_workspace);
     // FPN level 0: composed tcgen05 form (kpd_fpn0.cu; lateral 0 never materialised) in the fp32 / bf16 modes; the strict
-    // mode materialises lateral 0 and runs the fp32 CUDA-core conv.  bf16 mode stores the map as bf16 (half the write here and
-    // half the ROI-align read; the channel-attention pools still come from the fp32 accumulators).
+    // mode materialises lateral 0 and runs the fp32 CUDA-core conv.  The map stays fp32 in every mode: storing it as bf16 was
+    // measured (profiles/r02_error_attribution*.json) to add as much heat-map error as a whole bf16 head conv for 1% of the step.
     const bool strict = precision == KPD_PREC_FP32_SIMT;
     const bool composed = !strict;
     KPD_TRY(run_body(plan, d_images, B, S, strict, composed, ws, L, s));
@@ -179,7 +179,7 @@ extern "C" int kpd_backbone_fpn0(const kpd_plan* plan, int precision, const floa
         {
             ProfScope ps("fpn0_conv", s);
             KPD_TRY(fpn0_fused(plan, reinterpret_cast<const float*>(ws + L.scratch + sm.f0_tf32), reinterpret_cast<const float*>(ws + L.scratch + sm.lat1),
-                               ws + L.fpn0, precision == KPD_PREC_BF16 ? 1 : 0, pool_part, B, S, s));
+                               reinterpret_cast<float*>(ws + L.fpn0), pool_part, B, S, s));
         }
         KPD_TRY(run_pool_final(pool_part, B, fpn0_fused_parts(S), H0 * H0, reinterpret_cast<float*>(ws + L.pool_avg), reinterpret_cast<float*>(ws + L.pool_max), s));
         return 0;
@@ -226,7 +226,7 @@ extern "C" int kpd_roi_head(const kpd_plan* plan, int precision, int B, int S, c
     KPD_CUDA(cudaMemsetAsync(d_keypoints, 0, sizeof(float) * (size_t)n_max * K * 2, s));
     KPD_CUDA(cudaMemsetAsync(d_visibilities, 0, sizeof(float) * (size_t)n_max * K * 3, s));
     KPD_TRY(run_build_rois(d_boxes, B, P, ws, L, s));
-    KPD_TRY(run_roi_align(B, S, n_max, topk, precision == KPD_PREC_BF16 ? 1 : 0, ws, L, s));
+    KPD_TRY(run_roi_align(B, S, n_max, topk, ws, L, s));
     KPD_TRY(run_head_stack(plan, precision, B, S, n_max, ws, L, d_heatmap, s));
     DecodeArgs a{};
     a.hm = d_heatmap; a.maps = (int64_t)n_max * K; a.K = K; a.H = 56; a.W = 56; a.inv_temp = 1.f;

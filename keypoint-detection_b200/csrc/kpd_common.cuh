@@ -130,7 +130,7 @@ ScratchMap scratch_map(int B, int S, int n_rois);
 // ---- launchers implemented across the .cu files (all enqueue on `s`, return 0 / cudaError) ----
 int run_body(const kpd_plan* p, const float* images, int B, int S, int strict_fp32, int want_f0_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
 int run_fpn_laterals(const kpd_plan* p, int B, int S, int round_tf32, int strict_fp32, int composed, char* ws, const kpd_workspace_layout& L, cudaStream_t s);
-int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, void* out, int out_bf16, float* pool_part, int B, int S, cudaStream_t s);
+int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, float* out, float* pool_part, int B, int S, cudaStream_t s);
 int fpn0_fused_parts(int S);
 int run_pools(const float* fpn0, int B, int HW, float* avg, float* mx, float* scratch, cudaStream_t s);
 int run_pool_final(const float* partials, int B, int parts, int HW, float* avg, float* mx, cudaStream_t s);

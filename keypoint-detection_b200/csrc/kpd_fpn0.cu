@@ -30,7 +30,6 @@ struct Fpn0Params {
     int stages, total_groups, parts;   // parts = pooling partials per image = tiles_cy * tiles_cx * 16
     int mat_base[16];                  // first W2 matrix of sub-position sp = py*4 + px
     const float* bias; float* out; float* pool_part;
-    int out_bf16;                      // 1: `out` is bf16 [B][H0][W0][128] (bf16 mode: halves the write and the ROI-align read); pools stay fp32
     int skip;                          // timing attribution only (KPD_FPN0_SKIP): 1 no part (A), 2 no part (B), 4 no output stores, 8 no pooling
 };
 
@@ -39,7 +38,6 @@ constexpr int F0_EPI_WARPS = 8 /* 4 per tile of a group */, F0_RS = 36 /* padded
 __device__ __forceinline__ int f0_first(int p) { return p == 0 ? -1 : 0; }            // first coarse-neighbour offset along an axis
 __device__ __forceinline__ int f0_count(int p) { return (p == 0 || p == 3) ? 2 : 1; }   // neighbours along an axis
 
-template <bool OB16>                  // OB16: bf16 output
 __global__ void __launch_bounds__(F0_THREADS, 1)
 fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmL,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const Fpn0Params p) {
@@ -206,12 +204,8 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
                 const int n_w = pair * 2 + (lg >> 1), cy_w = cyt * 4 + ((lg & 1) << 1);     // image / first coarse row of this warp's 32 rows
                 float* rt = red + (warp - 2) * (32 * F0_RS);
                 float* wr = wred + ti * (8 * 128);
-                // transposed read-back: fp32 output -> lane = (row lane/8 of 4, 4 channels lane%8), 8 passes, a warp store = four
-                // 128-byte lines; bf16 output -> lane = (row lane/4 of 8, 8 channels lane%4), 4 passes, a warp store = eight 64-byte
-                // half lines (16 B per lane) -- the same number of bytes per store instruction in both forms
-                constexpr int RP = OB16 ? 8 : 4;                   // rows per pass
-                constexpr int CL = OB16 ? 8 : 4;                   // channels per lane
-                const int rrp = OB16 ? (lane >> 2) : (lane >> 3), q = OB16 ? (lane & 3) : (lane & 7);
+                // transposed read-back: lane = (row lane/8 of 4, 4 channels lane%8), 8 passes: a warp store = four 128-byte lines
+                const int rr4 = lane >> 3, q = lane & 7;
                 for (int c0 = 0; c0 < 128; c0 += 32) {
                     uint32_t r[32];
                     tc_ld32(taddr + c0, r);
@@ -226,58 +220,31 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
                         *reinterpret_cast<float4*>(rt + lane * F0_RS + 4 * j) = v;
                     }
                     __syncwarp();
-                    float sm[8], mx[8];
+                    float4 sm4 = make_float4(0.f, 0.f, 0.f, 0.f), mx4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int e = 0; e < 8; e++) { sm[e] = 0.f; mx[e] = 0.f; }
-#pragma unroll
-                    for (int it = 0; it < 32 / RP; it++) {
-                        const int rr = it * RP + rrp;                                        // tile row within this warp's 32
+                    for (int it = 0; it < 8; it++) {
+                        const int rr = it * 4 + rr4;                                         // tile row within this warp's 32
                         const int cx_r = cxt * 16 + (rr & 15), cy_r = cy_w + (rr >> 4);
-                        const float4 x0 = *reinterpret_cast<const float4*>(rt + rr * F0_RS + CL * q);
-                        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if constexpr (OB16) x1 = *reinterpret_cast<const float4*>(rt + rr * F0_RS + CL * q + 4);
+                        const float4 x = *reinterpret_cast<const float4*>(rt + rr * F0_RS + 4 * q);
                         if (n_w < p.B && cx_r < p.Wc) {
                             if (!(p.skip & 8)) {                                             // values are >= 0 after the ReLU
-                                sm[0] += x0.x; sm[1] += x0.y; sm[2] += x0.z; sm[3] += x0.w;
-                                mx[0] = fmaxf(mx[0], x0.x); mx[1] = fmaxf(mx[1], x0.y); mx[2] = fmaxf(mx[2], x0.z); mx[3] = fmaxf(mx[3], x0.w);
-                                if constexpr (OB16) {
-                                    sm[4] += x1.x; sm[5] += x1.y; sm[6] += x1.z; sm[7] += x1.w;
-                                    mx[4] = fmaxf(mx[4], x1.x); mx[5] = fmaxf(mx[5], x1.y); mx[6] = fmaxf(mx[6], x1.z); mx[7] = fmaxf(mx[7], x1.w);
-                                }
+                                sm4.x += x.x; sm4.y += x.y; sm4.z += x.z; sm4.w += x.w;
+                                mx4.x = fmaxf(mx4.x, x.x); mx4.y = fmaxf(mx4.y, x.y); mx4.z = fmaxf(mx4.z, x.z); mx4.w = fmaxf(mx4.w, x.w);
                             }
-                            if (!(p.skip & 4)) {
-                                const size_t o = (((size_t)n_w * p.H0 + (4 * cy_r + py)) * p.W0 + (4 * cx_r + px)) * 128 + c0 + CL * q;
-                                if constexpr (OB16) {
-                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(x0.x, x0.y), h1 = __floats2bfloat162_rn(x0.z, x0.w);
-                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(x1.x, x1.y), h3 = __floats2bfloat162_rn(x1.z, x1.w);
-                                    uint4 pk;
-                                    pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                    pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pk;
-                                } else {
-                                    *reinterpret_cast<float4*>(p.out + o) = x0;
-                                }
-                            }
+                            if (!(p.skip & 4))
+                                *reinterpret_cast<float4*>(p.out + (((size_t)n_w * p.H0 + (4 * cy_r + py)) * p.W0 + (4 * cx_r + px)) * 128 + c0 + 4 * q) = x;
                         }
                     }
-                    // combine the row groups: lanes that share q (xor over the row bits of the lane index)
 #pragma unroll
-                    for (int o = OB16 ? 4 : 8; o <= 16; o <<= 1) {
-#pragma unroll
-                        for (int e = 0; e < CL; e++) {
-                            sm[e] += __shfl_xor_sync(0xffffffffu, sm[e], o);
-                            mx[e] = fmaxf(mx[e], __shfl_xor_sync(0xffffffffu, mx[e], o));
-                        }
+                    for (int o = 8; o <= 16; o <<= 1) {                                      // combine the 4 row groups (lanes q, q+8, q+16, q+24)
+                        sm4.x += __shfl_xor_sync(0xffffffffu, sm4.x, o); sm4.y += __shfl_xor_sync(0xffffffffu, sm4.y, o);
+                        sm4.z += __shfl_xor_sync(0xffffffffu, sm4.z, o); sm4.w += __shfl_xor_sync(0xffffffffu, sm4.w, o);
+                        mx4.x = fmaxf(mx4.x, __shfl_xor_sync(0xffffffffu, mx4.x, o)); mx4.y = fmaxf(mx4.y, __shfl_xor_sync(0xffffffffu, mx4.y, o));
+                        mx4.z = fmaxf(mx4.z, __shfl_xor_sync(0xffffffffu, mx4.z, o)); mx4.w = fmaxf(mx4.w, __shfl_xor_sync(0xffffffffu, mx4.w, o));
                     }
-                    if (rrp == 0) {
-                        float* ws = wr + (lg * 2 + 0) * 128 + c0 + CL * q;
-                        float* wm = wr + (lg * 2 + 1) * 128 + c0 + CL * q;
-                        *reinterpret_cast<float4*>(ws) = make_float4(sm[0], sm[1], sm[2], sm[3]);
-                        *reinterpret_cast<float4*>(wm) = make_float4(mx[0], mx[1], mx[2], mx[3]);
-                        if constexpr (OB16) {
-                            *reinterpret_cast<float4*>(ws + 4) = make_float4(sm[4], sm[5], sm[6], sm[7]);
-                            *reinterpret_cast<float4*>(wm + 4) = make_float4(mx[4], mx[5], mx[6], mx[7]);
-                        }
+                    if (lane < 8) {
+                        *reinterpret_cast<float4*>(wr + (lg * 2 + 0) * 128 + c0 + 4 * q) = sm4;
+                        *reinterpret_cast<float4*>(wr + (lg * 2 + 1) * 128 + c0 + 4 * q) = mx4;
                     }
                     __syncwarp();
                 }
@@ -316,8 +283,8 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
 int fpn0_fused_parts(int S) { const int Hc = S / 8; return (Hc / 4) * ((Hc + 15) / 16) * 16; }
 
 // f0t: tf32-rounded stem output as 16 sub-position planes [qy*4+qx][NB][S/8][S/8][16] (NB = B rounded up to even); lat1: tf32-rounded lateral level 1 [B][S/8][S/8][128] (top-down sum included);
-// out: fpn0 [B][S/2][S/2][128] fp32 (or bf16 when out_bf16); pool_part: [B][fpn0_fused_parts(S)][2][128].  Buffers must extend one image past an odd B.
-int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, void* out, int out_bf16, float* pool_part, int B, int S, cudaStream_t s) {
+// out: fpn0 [B][S/2][S/2][128] fp32; pool_part: [B][fpn0_fused_parts(S)][2][128].  Buffers must extend one image past an odd B.
+int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, float* out, float* pool_part, int B, int S, cudaStream_t s) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
     if (S % 32 != 0 || !plan->fpn0c_w1 || !plan->fpn0c_w2) { set_error("fpn0_fused: unsupported size %d or missing composed weights", S); return KPD_ERR_UNSUPPORTED; }
@@ -335,7 +302,7 @@ int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, void* 
         const int py = sp >> 2, px = sp & 3;
         m += ((py == 0 || py == 3) ? 2 : 1) * ((px == 0 || px == 3) ? 2 : 1);
     }
-    p.bias = plan->fpn_conv[0].bias; p.out = static_cast<float*>(out); p.out_bf16 = out_bf16; p.pool_part = pool_part;
+    p.bias = plan->fpn_conv[0].bias; p.out = out; p.pool_part = pool_part;
     static const int skip_env = getenv("KPD_FPN0_SKIP") ? atoi(getenv("KPD_FPN0_SKIP")) : 0;
     p.skip = skip_env;
     const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * 128 + 4 * (F0_EPI_WARPS * 32 * F0_RS + 2 * 8 * 128) + 64;
@@ -383,15 +350,10 @@ int fpn0_fused(const kpd_plan* plan, const float* f0t, const float* lat1, void* 
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("fpn0_fused: cuTensorMapEncodeTiled(W2) failed: %d", (int)r); return KPD_ERR_STATE; }
     }
-    static uint64_t attr = 0, attr16 = 0;
+    static uint64_t attr = 0;
+    KPD_CUDA(ensure_smem_attr(fpn0_fused_kernel, 227 * 1024, attr));
     const int grid = std::min(p.total_groups, plan->sm_count);
-    if (out_bf16) {
-        KPD_CUDA(ensure_smem_attr(fpn0_fused_kernel<true>, 227 * 1024, attr16));
-        fpn0_fused_kernel<true><<<grid, F0_THREADS, smem, s>>>(tmF, tmL, tmW1, tmW2, p);
-    } else {
-        KPD_CUDA(ensure_smem_attr(fpn0_fused_kernel<false>, 227 * 1024, attr));
-        fpn0_fused_kernel<false><<<grid, F0_THREADS, smem, s>>>(tmF, tmL, tmW1, tmW2, p);
-    }
+    fpn0_fused_kernel<<<grid, F0_THREADS, smem, s>>>(tmF, tmL, tmW1, tmW2, p);
     KPD_LAUNCH_CHECK();
     return 0;
 }

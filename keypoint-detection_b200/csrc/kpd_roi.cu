@@ -8,10 +8,6 @@
 
 namespace kpd {
 
-// feature-map element -> float (the map is fp32, or bf16 in bf16 mode)
-__device__ __forceinline__ float ld_feat(const float* p) { return __ldg(p); }
-__device__ __forceinline__ float ld_feat(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
-
 // ------------------------------------------------------------------------------------------------
 // Order-preserving compaction of the non-zero boxes.  One block; images are walked in chunks of 1024 (thread = image) with a
 // block-wide exclusive scan of the per-image counts and a running carry, so any batch size works without dynamic shared memory.
@@ -66,8 +62,7 @@ __global__ void __launch_bounds__(1024) build_rois_kernel(const float* __restric
 // grid (ROI_PARTS, Nmax): each block handles 2 output rows; a warp handles one output pixel at a time with
 // lanes over channels (2 per lane) so the gather of one bilinear tap touches the 4 cache lines of one NHWC pixel.
 // Also emits per-block partial sum/max per channel for the head's channel attention.
-template <typename FT>
-__global__ void __launch_bounds__(256) roi_align_kernel(const FT* __restrict__ fpn0, const int32_t* __restrict__ topk,
+__global__ void __launch_bounds__(256) roi_align_kernel(const float* __restrict__ fpn0, const int32_t* __restrict__ topk,
                                                         const float* __restrict__ roi_box, const int32_t* __restrict__ roi_batch,
                                                         const int32_t* __restrict__ roi_count, float* __restrict__ roi_feat,
                                                         float* __restrict__ part, int H, int W) {
@@ -86,7 +81,7 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FT* __restrict__ f
     const int gh = (int)ceilf(rh / 56.f), gw = (int)ceilf(rw / 56.f);
     const float count = (float)max(gh * gw, 1);
     const int c0 = min(max(topk[b * KPD_TOPK + lane], 0), KPD_FPN_CH - 1), c1 = min(max(topk[b * KPD_TOPK + lane + 32], 0), KPD_FPN_CH - 1);   // (a caller-supplied override cannot index out of the pixel)
-    const FT* fb = fpn0 + (int64_t)b * H * W * 128;
+    const float* fb = fpn0 + (int64_t)b * H * W * 128;
     float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
     const int row0 = blockIdx.x * 2;
     for (int q = warp; q < 2 * 56; q += 8) {
@@ -102,10 +97,10 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const FT* __restrict__ f
             if (xl >= W - 1) { xl = xh = W - 1; x = (float)xl; } else xh = xl + 1;
             const float ly = y - (float)yl, hy = 1.f - ly, lx = x - (float)xl, hx = 1.f - lx;
             const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-            const FT* p1 = fb + ((int64_t)yl * W + xl) * 128; const FT* p2 = fb + ((int64_t)yl * W + xh) * 128;
-            const FT* p3 = fb + ((int64_t)yh * W + xl) * 128; const FT* p4 = fb + ((int64_t)yh * W + xh) * 128;
-            a0 += w1 * ld_feat(p1 + c0) + w2 * ld_feat(p2 + c0) + w3 * ld_feat(p3 + c0) + w4 * ld_feat(p4 + c0);
-            a1 += w1 * ld_feat(p1 + c1) + w2 * ld_feat(p2 + c1) + w3 * ld_feat(p3 + c1) + w4 * ld_feat(p4 + c1);
+            const float* p1 = fb + ((int64_t)yl * W + xl) * 128; const float* p2 = fb + ((int64_t)yl * W + xh) * 128;
+            const float* p3 = fb + ((int64_t)yh * W + xl) * 128; const float* p4 = fb + ((int64_t)yh * W + xh) * 128;
+            a0 += w1 * __ldg(p1 + c0) + w2 * __ldg(p2 + c0) + w3 * __ldg(p3 + c0) + w4 * __ldg(p4 + c0);
+            a1 += w1 * __ldg(p1 + c1) + w2 * __ldg(p2 + c1) + w3 * __ldg(p3 + c1) + w4 * __ldg(p4 + c1);
         };
         if (gh <= 2 && gw <= 2) {          // S=224 (ROI <= 112 px): fully unrolled so all 32 gathers of a pixel are in flight
 #pragma unroll
@@ -178,8 +173,8 @@ __device__ __forceinline__ void ra_axis(float start, float bin, int g, int size,
     }
 }
 
-template <int NR, typename FT>                           // NR >= rows / columns a bin can touch (g + 1); FT = float | bf16 feature map
-__global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict__ fpn0, const int32_t* __restrict__ topk,
+template <int NR>                                        // NR >= rows / columns a bin can touch (g + 1)
+__global__ void __launch_bounds__(256) roi_align_sep_kernel(const float* __restrict__ fpn0, const int32_t* __restrict__ topk,
                                                             const float* __restrict__ roi_box, const int32_t* __restrict__ roi_batch,
                                                             const int32_t* __restrict__ roi_count, float* __restrict__ roi_feat,
                                                             float* __restrict__ part, int H, int W) {
@@ -230,7 +225,7 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict
     __syncthreads();
     const int xs0 = span[0], ncol = span[1] - span[0] + 1;
     const int c0 = min(max(topk[b * KPD_TOPK + lane], 0), KPD_FPN_CH - 1), c1 = min(max(topk[b * KPD_TOPK + lane + 32], 0), KPD_FPN_CH - 1);   // (a caller-supplied override cannot index out of the pixel)
-    const FT* fb = fpn0 + (int64_t)b * H * W * 128;
+    const float* fb = fpn0 + (int64_t)b * H * W * 128;
     float s0 = 0.f, s1 = 0.f, m0 = -INFINITY, m1 = -INFINITY;
     for (int r = 0; r < 2; r++) {
         const int ph = row0 + r, yf = yfirst[r], nr = ycount[r];
@@ -243,10 +238,10 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict
             float v0[CU][NR], v1[CU][NR];
 #pragma unroll
             for (int u = 0; u < CU; u++) {
-                const FT* px = fb + ((int64_t)yf * W + xs0 + min(cb + u, ncol - 1)) * 128;
+                const float* px = fb + ((int64_t)yf * W + xs0 + min(cb + u, ncol - 1)) * 128;
 #pragma unroll
                 for (int j = 0; j < NR; j++) {
-                    if (j < nr) { v0[u][j] = ld_feat(px + (int64_t)j * W * 128 + c0); v1[u][j] = ld_feat(px + (int64_t)j * W * 128 + c1); }
+                    if (j < nr) { v0[u][j] = __ldg(px + (int64_t)j * W * 128 + c0); v1[u][j] = __ldg(px + (int64_t)j * W * 128 + c1); }
                     else { v0[u][j] = 0.f; v1[u][j] = 0.f; }
                 }
             }
@@ -286,8 +281,7 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const FT* __restrict
     }
 }
 
-template <typename FT>
-static int launch_roi_align(const FT* fpn0, const int32_t* topk, const float* roi_box, const int32_t* roi_batch, const int32_t* roi_count,
+static int launch_roi_align(const float* fpn0, const int32_t* topk, const float* roi_box, const int32_t* roi_batch, const int32_t* roi_count,
                             float* roi_feat, float* part, int n, int H, int W, cudaStream_t s) {
     static const bool legacy = getenv("KPD_ROI_SAMPLEWISE") != nullptr;      // sample-by-sample form, kept for A/B checks
     const size_t dyn = sizeof(float) * (size_t)W * 64;
@@ -295,14 +289,14 @@ static int launch_roi_align(const FT* fpn0, const int32_t* topk, const float* ro
     if (!legacy && gmax <= RA_MAXG && dyn <= 160 * 1024) {
         static uint64_t attr4 = 0, attr8 = 0;
         if (gmax + 1 <= 4) {
-            KPD_CUDA(ensure_smem_attr(roi_align_sep_kernel<4, FT>, 160 * 1024, attr4));    // set once per device: the maximum any call may ask for
-            roi_align_sep_kernel<4, FT><<<dim3(ROI_PARTS, n), 256, dyn, s>>>(fpn0, topk, roi_box, roi_batch, roi_count, roi_feat, part, H, W);
+            KPD_CUDA(ensure_smem_attr(roi_align_sep_kernel<4>, 160 * 1024, attr4));    // set once per device: the maximum any call may ask for
+            roi_align_sep_kernel<4><<<dim3(ROI_PARTS, n), 256, dyn, s>>>(fpn0, topk, roi_box, roi_batch, roi_count, roi_feat, part, H, W);
         } else {
-            KPD_CUDA(ensure_smem_attr(roi_align_sep_kernel<8, FT>, 160 * 1024, attr8));
-            roi_align_sep_kernel<8, FT><<<dim3(ROI_PARTS, n), 256, dyn, s>>>(fpn0, topk, roi_box, roi_batch, roi_count, roi_feat, part, H, W);
+            KPD_CUDA(ensure_smem_attr(roi_align_sep_kernel<8>, 160 * 1024, attr8));
+            roi_align_sep_kernel<8><<<dim3(ROI_PARTS, n), 256, dyn, s>>>(fpn0, topk, roi_box, roi_batch, roi_count, roi_feat, part, H, W);
         }
     } else {
-        roi_align_kernel<FT><<<dim3(ROI_PARTS, n), 256, 0, s>>>(fpn0, topk, roi_box, roi_batch, roi_count, roi_feat, part, H, W);
+        roi_align_kernel<<<dim3(ROI_PARTS, n), 256, 0, s>>>(fpn0, topk, roi_box, roi_batch, roi_count, roi_feat, part, H, W);
     }
     KPD_LAUNCH_CHECK();
     return 0;
@@ -444,14 +438,12 @@ int run_build_rois(const float* boxes, int B, int P, char* ws, const kpd_workspa
     return 0;
 }
 
-int run_roi_align(int B, int S, int n_max, const int32_t* topk, int feat_bf16, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
+int run_roi_align(int B, int S, int n_max, const int32_t* topk, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {
     ProfScope ps("roi_align", s);
     const ScratchMap sm = scratch_map(B, S, n_max + 1);
-    const float* box = reinterpret_cast<const float*>(ws + L.roi_box);
-    const int32_t* rb = reinterpret_cast<const int32_t*>(ws + L.roi_batch), *rc = reinterpret_cast<const int32_t*>(ws + L.roi_count);
-    float* out = reinterpret_cast<float*>(ws + L.roi_feat), *part = reinterpret_cast<float*>(ws + L.scratch + sm.roi_part);
-    if (feat_bf16) return launch_roi_align(reinterpret_cast<const __nv_bfloat16*>(ws + L.fpn0), topk, box, rb, rc, out, part, n_max, S / 2, S / 2, s);
-    return launch_roi_align(reinterpret_cast<const float*>(ws + L.fpn0), topk, box, rb, rc, out, part, n_max, S / 2, S / 2, s);
+    return launch_roi_align(reinterpret_cast<const float*>(ws + L.fpn0), topk, reinterpret_cast<const float*>(ws + L.roi_box),
+        reinterpret_cast<const int32_t*>(ws + L.roi_batch), reinterpret_cast<const int32_t*>(ws + L.roi_count),
+        reinterpret_cast<float*>(ws + L.roi_feat), reinterpret_cast<float*>(ws + L.scratch + sm.roi_part), n_max, S / 2, S / 2, s);
 }
 
 int run_head_attention(const kpd_plan* p, int B, int S, int n_max, int out_bf16, int round_tf32, char* ws, const kpd_workspace_layout& L, cudaStream_t s) {

@@ -97,7 +97,7 @@ def stage_views(ws, L, batch, size, n_rois, precision):
     c = [16, 24, 48, 576]
     out = {f"feat{i}": view(ws, L.feat[i], (batch, h[i], h[i], c[i]), torch.float32) for i in range(4)}
     out["lateral0"] = view(ws, L.lateral0, (batch, h[0], h[0], 128), torch.float32)
-    out["fpn0"] = view(ws, L.fpn0, (batch, h[0], h[0], 128), elt)      # bf16 mode stores the FPN-0 map as bf16
+    out["fpn0"] = view(ws, L.fpn0, (batch, h[0], h[0], 128), torch.float32)
     out["pool_avg"] = view(ws, L.pool_avg, (batch, 128), torch.float32)
     out["pool_max"] = view(ws, L.pool_max, (batch, 128), torch.float32)
     out["scores"] = view(ws, L.scores, (batch, 128), torch.float32)
