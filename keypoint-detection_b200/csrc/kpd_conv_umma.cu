@@ -12,7 +12,10 @@
 //     (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1), tcgen05.commit releases
 //     shared-memory stages / publishes accumulators through mbarriers.
 //   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc),
-//     warps 2-5 epilogue (tcgen05.ld -> +bias -> ReLU -> bf16/fp32 NHWC stores).
+//     warps 2.. epilogue: tcgen05.ld -> +bias -> ReLU -> bf16/fp32 rows into a 128B-swizzled shared-memory staging tile ->
+//     one TMA tensor store per (warp, 128 bytes of channels): full-line writes, out-of-image pixels clipped by the TMA unit
+//     (a row-per-thread st.global epilogue issues 32 half-empty sector requests per instruction and made the K = 576
+//     conv 64->256 epilogue-bound at 2.7x its MMA time, profiles/r02_conv1_sass_summary_before_tma_store.txt).
 #include "kpd_tma.cuh"
 #include <stdlib.h>
 
@@ -82,6 +85,12 @@ __device__ __forceinline__ void epi_store(const ConvParams& p, const float (&v)[
 }
 
 constexpr int UMMA_THREADS = 192;
+constexpr int TS_WARP_BYTES = 4096;      // TMA-store staging: 32 pixel rows x 128 bytes of channels per epilogue warp, double-buffered
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 
 // MT = M-tiles (128 pixels each) sharing one weight stage, RB = bytes of K per shared-memory row (128, or 64 for the
 // 16-channel fp32 lateral); both compile-time so that the single MMA-issuing thread runs a fully unrolled, lean loop
@@ -89,22 +98,27 @@ constexpr int UMMA_THREADS = 192;
 // EW = epilogue warps: 4 (one per TMEM lane group) or 8 (two per lane group, each draining half of the output channels --
 // the epilogue of a tile is a dependent chain of tcgen05.ld -> bias/ReLU -> convert -> stores per 32-channel chunk, and with
 // K as short as 576 (head conv 64->256) one warp per lane group cannot drain a tile in the time the MMAs need for the next).
-template <bool BF16, int MT, int RB, int EW>
+// TS = TMA-store epilogue (plain convs: no fused pooling / residual / final 1x1, NHWC output).
+template <bool BF16, int MT, int RB, int EW, bool TS>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                 const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages x (A | B)] | barriers | tmem slot | bias
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // carve: [stages x (A | B)] | store staging (TS) | barriers | tmem slot | bias
+    // (offset arithmetic on the __shared__ array, not an integer round trip: the bias / weight reads of the epilogue must compile
+    //  to LDS -- as generic loads they were the top stall of the epilogue warps)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int A_BYTES = 128 * RB;
     const int B_BYTES = p.Cout * RB;
     const int STAGE_BYTES = MT * A_BYTES + B_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
+    uint8_t* stage_out = smem + (size_t)p.stages * STAGE_BYTES;                 // [EW][2][TS_WARP_BYTES], 1024-byte aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (TS ? EW * 2 * TS_WARP_BYTES : 0));
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
     float* red = sbias + p.Cout;                      // pooling only: [4 warps][32][33] transpose tiles
     float* wred = red + 4 * 32 * 33;                  // pooling only: [4 warps][2][Cout] per-warp channel sum / max
-    float* finw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sbias + p.Cout) + 15) & ~uintptr_t(15));   // fused final 1x1 only: [64][FIN_KP] + bias [FIN_KP]
+    float* finw = sbias + p.Cout;                     // fused final 1x1 only: [64][FIN_KP] + bias [FIN_KP] (16-byte aligned: every block before it is)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
@@ -119,6 +133,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (TS) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
         for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -206,15 +221,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {                                            // ---------------- epilogue warps 2..5
         const int lg = warp & 3;                        // TMEM lane group this warp may access
-        const int chalf = (warp - 2) >> 2;              // EW == 8: which half of the output channels
-        const int cbeg = EW == 8 ? chalf * (p.Cout >> 1) : 0, cend = EW == 8 ? cbeg + (p.Cout >> 1) : p.Cout;
+        // EW == 8: two warps per lane group.  They split the M-tiles of a group (fused final 1x1: MT = 4, two tiles each) or
+        // the output channels (TMA-store epilogue)
+        const int whalf = (warp - 2) >> 2;
+        const bool split_tiles = EW == 8 && !TS;
+        const int cbeg = (EW == 8 && TS) ? whalf * (p.Cout >> 1) : 0, cend = (EW == 8 && TS) ? cbeg + (p.Cout >> 1) : p.Cout;
+        const int ti_beg = split_tiles ? whalf * (MT / 2) : 0, ti_end = split_tiles ? ti_beg + MT / 2 : MT;
         const int row = lg * 32 + lane;
         const int rw = row % p.tw, rh = (row / p.tw) % p.th, rn = row / (p.tw * p.th);
+        // TMA-store epilogue: this warp's 32 accumulator rows are the pixel box {tw, 32 / tw} of instance rn0 at row offset rh0
+        const int rh0 = ((lg * 32) / p.tw) % p.th, rn0 = (lg * 32) / (p.tw * p.th);
+        uint8_t* sbuf = stage_out + (size_t)(warp - 2) * 2 * TS_WARP_BYTES;
+        uint32_t nstore = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
           mbar_wait_warp(tfull_bar(acc), acc_phase, lane);
           tc_fence_after();
-          for (int ti = 0; ti < MT; ti++) {
+          for (int ti = ti_beg; ti < ti_end; ti++) {
             const int tile = grp * MT + ti;
             if (tile >= total_tiles) break;
             const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
@@ -222,6 +245,61 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool valid = (w < p.W) && (h < p.H) && (n < n_live);
             const size_t pix = ((size_t)n * p.H + h) * p.W + w;
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((acc * MT + ti) * p.Cout);
+            if constexpr (TS) {
+                // 128 bytes of output channels (64 bf16 / 32 fp32) per pixel row -> swizzled staging rows -> one tensor store
+                constexpr int SC = BF16 ? 64 : 32;
+                for (int c0 = cbeg; c0 < cend; c0 += SC) {
+                    uint8_t* buf = sbuf + (nstore & 1u) * TS_WARP_BYTES;
+                    // the store that read this buffer two chunks ago has drained it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+                    for (int hh = 0; hh < SC / 32; hh++) {
+                        uint32_t r[32];
+                        tc_ld32(taddr + c0 + 32 * hh, r);
+                        tc_wait_ld();
+                        const float4* b4 = reinterpret_cast<const float4*>(sbias + c0 + 32 * hh);
+                        float v[32];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 bb = b4[q];
+                            v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + bb.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+                            v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            float x = p.act == ACT_RELU ? fmaxf(v[j], 0.f) : v[j];
+                            v[j] = p.round_out_tf32 ? tf32_rna(x) : x;
+                        }
+                        if constexpr (BF16) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {          // 16-byte chunk 4*hh + q of the row: channels 8q .. 8q+7 of this half
+                                uint4 u;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]);
+                                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]);
+                                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+                                u.x = *reinterpret_cast<uint32_t*>(&t0); u.y = *reinterpret_cast<uint32_t*>(&t1);
+                                u.z = *reinterpret_cast<uint32_t*>(&t2); u.w = *reinterpret_cast<uint32_t*>(&t3);
+                                *reinterpret_cast<uint4*>(rowp + (((4 * hh + q) ^ (lane & 7)) << 4)) = u;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; q++)
+                                *reinterpret_cast<float4*>(rowp + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the TMA unit
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&tmO, smem_u32(buf), c0, iw * p.tw, ih * p.th + rh0, in * p.tn + rn0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    nstore++;
+                }
+                continue;
+            }
             if (p.fin_w) {
                 // fused final_layer[3] + sigmoid: the thread owns one pixel, its 64 conv outputs arrive as two 32-column TMEM
                 // loads, the 17 joint logits accumulate in registers (weights = shared-memory float4 broadcasts) and leave as
@@ -305,6 +383,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (TS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every tensor store has completed
     }
     tc_fence_before();
     __syncthreads();
@@ -491,21 +570,25 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         if (c.cout != 64 || pool_part || res) { set_error("conv_dense_umma: the fused final 1x1 needs a plain 64-channel conv"); return KPD_ERR_UNSUPPORTED; }
         p.fin_w = fin->w; p.fin_b = fin->b; p.fin_out = fin->out; p.fin_slot = fin->slot;
     }
-    static const int mt_env = getenv("KPD_CONV_MT") ? atoi(getenv("KPD_CONV_MT")) : 0;
     int mt = 1;                                          // M-tiles per weight stage: as many as TMEM (512 columns, double-buffered) allows, <= 4
     while (mt < 4 && 2 * (mt * 2) * c.cout <= 512) mt *= 2;
-    if (mt_env > 0) mt = std::min(mt, mt_env);
     if (row_bytes == 64) mt = 1;
     p.mt = mt;
     if (pool_part && p.tn != 1) { set_error("conv_dense_umma: fused pooling needs W %% 16 == 0 and H %% 8 == 0"); return KPD_ERR_UNSUPPORTED; }
+    // Epilogue form: TMA tensor stores for the plain NHWC convs (head convs 64->256, 256->256; the FPN levels 1-3); the fused
+    // variants (pooling, residual, final 1x1) keep their register epilogues; the fused final 1x1 runs two epilogue warps per
+    // TMEM lane group, each on half of the group's M-tiles (its 64x17 FMAs per pixel made a 4-warp epilogue the bottleneck).
+    const bool ts = !fin && !pool_part && !res && row_bytes == 128 && c.cout % (prec_bf16 && out_bf16 ? 64 : 32) == 0 && (out_bf16 != 0) == (prec_bf16 != 0) && 32 % p.tw == 0;
+    const bool ew8 = fin && mt == 4;
+    const int ew = ew8 ? 8 : 4;
     const int stage_bytes = mt * 128 * row_bytes + c.cout * row_bytes;
-    const int misc = 1024 /*align*/ + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0) + (fin ? 4 * 65 * FIN_KP + 16 : 0);
+    const int misc = 1024 /*align*/ + (ts ? ew * 2 * TS_WARP_BYTES : 0) + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0) + (fin ? 4 * 65 * FIN_KP + 16 : 0);
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + misc;
 
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO;
     {
         cuuint64_t dims[4] = {(cuuint64_t)c.cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)c.cin * elt, (cuuint64_t)W * c.cin * elt, (cuuint64_t)H * W * c.cin * elt};
@@ -528,30 +611,39 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return KPD_ERR_STATE; }
     }
+    tmO = tmB;                                           // placeholder when the epilogue stores from registers
+    if (ts) {
+        // output tensor [N][H][W][Cout] as seen by one epilogue warp: 128 bytes of channels x its 32 pixels (tw x 32/tw); pixels
+        // outside the image (partial edge tiles) and instances past N are clipped by the TMA unit
+        const int oelt = out_bf16 ? 2 : 4;
+        cuuint64_t dims[4] = {(cuuint64_t)c.cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)c.cout * oelt, (cuuint64_t)W * c.cout * oelt, (cuuint64_t)H * W * c.cout * oelt};
+        cuuint32_t box[4] = {(cuuint32_t)(128 / oelt), (cuuint32_t)p.tw, (cuuint32_t)(32 / p.tw), 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmO, out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return KPD_ERR_STATE; }
+    }
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
     const int grid = std::min((total_tiles + mt - 1) / mt, plan->sm_count);
-#define KPD_LAUNCH_UMMA(BF, MTV, RBV)                                                                                     \
+    static uint64_t attr[16] = {};
+#define KPD_LAUNCH_UMMA(BF, MTV, RBV, EWV, TSV, SLOT)                                                                     \
     do {                                                                                                                  \
-        if (ew8) {                                                                                                        \
-            KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BF, MTV, RBV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            conv_umma_kernel<BF, MTV, RBV, 8><<<grid, 64 + 32 * 8, smem, s>>>(tmA, tmB, p);                               \
-        } else {                                                                                                          \
-            KPD_CUDA(cudaFuncSetAttribute(conv_umma_kernel<BF, MTV, RBV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            conv_umma_kernel<BF, MTV, RBV, 4><<<grid, 64 + 32 * 4, smem, s>>>(tmA, tmB, p);                               \
-        }                                                                                                                 \
+        KPD_CUDA(ensure_smem_attr(conv_umma_kernel<BF, MTV, RBV, EWV, TSV>, 227 * 1024, attr[SLOT]));                     \
+        conv_umma_kernel<BF, MTV, RBV, EWV, TSV><<<grid, 64 + 32 * EWV, smem, s>>>(tmA, tmB, tmO, p);                     \
     } while (0)
-    // KPD_CONV_EW8=1: two epilogue warps per TMEM lane group (not with fused pooling, whose per-warp reductions assume 4 warps).
-    // Measured neutral on the head convs (0.277 vs 0.266 ms for 64->256): their short-K tiles are bound by operand and
-    // output traffic, not by the epilogue's dependent chain, so the default stays at 4.
-    static const bool ew_env8 = getenv("KPD_CONV_EW8") != nullptr;
-    const bool ew8 = ew_env8 && !pool_part && (c.cout % 64 == 0);
     if (row_bytes == 64) {
         if (prec_bf16 || mt != 1) { set_error("conv_dense_umma: 64-byte K rows are built for tf32, mt=1"); return KPD_ERR_UNSUPPORTED; }
-        KPD_LAUNCH_UMMA(false, 1, 64);
+        KPD_LAUNCH_UMMA(false, 1, 64, 4, false, 0);
+    } else if (ew8) {
+        if (prec_bf16) KPD_LAUNCH_UMMA(true, 4, 128, 8, false, 1); else KPD_LAUNCH_UMMA(false, 4, 128, 8, false, 2);
+    } else if (ts) {
+        if (prec_bf16) { if (mt == 4) KPD_LAUNCH_UMMA(true, 4, 128, 4, true, 3); else if (mt == 2) KPD_LAUNCH_UMMA(true, 2, 128, 4, true, 4); else KPD_LAUNCH_UMMA(true, 1, 128, 4, true, 5); }
+        else { if (mt == 4) KPD_LAUNCH_UMMA(false, 4, 128, 4, true, 6); else if (mt == 2) KPD_LAUNCH_UMMA(false, 2, 128, 4, true, 7); else KPD_LAUNCH_UMMA(false, 1, 128, 4, true, 8); }
     } else if (prec_bf16) {
-        if (mt == 4) KPD_LAUNCH_UMMA(true, 4, 128); else if (mt == 2) KPD_LAUNCH_UMMA(true, 2, 128); else KPD_LAUNCH_UMMA(true, 1, 128);
+        if (mt == 4) KPD_LAUNCH_UMMA(true, 4, 128, 4, false, 9); else if (mt == 2) KPD_LAUNCH_UMMA(true, 2, 128, 4, false, 10); else KPD_LAUNCH_UMMA(true, 1, 128, 4, false, 11);
     } else {
-        if (mt == 4) KPD_LAUNCH_UMMA(false, 4, 128); else if (mt == 2) KPD_LAUNCH_UMMA(false, 2, 128); else KPD_LAUNCH_UMMA(false, 1, 128);
+        if (mt == 4) KPD_LAUNCH_UMMA(false, 4, 128, 4, false, 12); else if (mt == 2) KPD_LAUNCH_UMMA(false, 2, 128, 4, false, 13); else KPD_LAUNCH_UMMA(false, 1, 128, 4, false, 14);
     }
 #undef KPD_LAUNCH_UMMA
     KPD_LAUNCH_CHECK();

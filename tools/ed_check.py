@@ -35,7 +35,7 @@ lib.kpd_profile_enable(1)
 for _ in range(5):
     m.predict({"image": x, "bboxes": boxes})
 torch.cuda.synchronize()
-for tag in ("body", "body.stem", "body.expand_dw", "body.pointwise", "body.depthwise", "body.se") + tuple(f"ed.f{i}" for i in range(2, 12)):
+for tag in ("body", "body.stem", "body.expand_dw", "body.pointwise", "body.depthwise", "body.se") + tuple(f"ed.f{i}" for i in range(2, 12)) + ("fpn_laterals",):
     t, n = C.c_double(0), C.c_int64(0)
     if lib.kpd_profile_read(tag.encode(), C.byref(t), C.byref(n)) == 0 and n.value:
         print(f"{tag}: {t.value / 5:.4f} ms/step over {n.value // 5} launches")
