@@ -248,13 +248,21 @@ def read_profile(lib, prof_steps):
 
 
 def profile_kernels(lib, step, prof_steps=5):
-    """per-kernel CUDA-event timing (library-side events on the launching stream), outside the timed region"""
+    """per-stage CUDA-event timing (library-side events on the launching stream), outside the timed region.  Two passes: stage
+    totals with one event pair per stage (the launches of a stage stay back to back), then the nested per-part tags -- those
+    events sit between the short trunk launches and cost idle time, so the parts can add up to more than their stage."""
     lib.kpd_profile_enable(1)
     for _ in range(prof_steps):
         step()
     torch.cuda.synchronize()
     kern = read_profile(lib, prof_steps)
+    lib.kpd_profile_enable(2)
+    for _ in range(prof_steps):
+        step()
+    torch.cuda.synchronize()
+    parts = read_profile(lib, prof_steps)
     lib.kpd_profile_enable(0)
+    kern.update({k: v for k, v in parts.items() if "." in k})
     return kern
 
 

@@ -169,7 +169,9 @@ const char* kpd_last_error(void);
 int  kpd_abi_version(void);
 /* number of kernel launches enqueued by this thread since the last call with reset!=0 (bench claim) */
 int64_t kpd_launch_count(int reset);
-/* CUDA-event timing of tagged kernels inside the library (bench roofline): enable, then read back */
+/* CUDA-event timing of tagged regions inside the library (bench roofline): enable, then read back.
+   on = 1: one event pair per stage ("body", "fpn0_conv", "head_conv2", ...); on = 2: also the nested "stage.part" tags
+   (their events sit between short launches and inflate the enclosing stage's total); on = 0: off */
 int  kpd_profile_enable(int on);
 int  kpd_profile_read(const char* tag, double* total_ms, int64_t* launches);
 

@@ -9,6 +9,8 @@
 
 namespace kpd {
 
+__device__ __forceinline__ uint32_t smem_u32_generic(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 int depthwise_batched(const MBBlock& m, const float* in, float* out, float* pool, size_t pool_capacity, int* pool_parts, int B, int H, int sm_count, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
@@ -161,90 +163,153 @@ int pointwise(const float* in, const float* w, const float* bias, float* out, in
     return launch_pw(a, s);
 }
 
-// SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 ).
-// One CTA per SE_IMG images (the weight matrices are read once per CTA, not once per image: at C = 576 they are 2 x 332 KB).
-// A layer is spread over (4-output group, k-slice) threads with the S slices of a group in ADJACENT lanes: every thread
-// streams K/S float4 weight rows (8 in flight), and the slices are combined with a shuffle butterfly -- the layer is a
-// latency chain of K/(8*S) dependent load batches instead of K/8, with no shared-memory partials.
-constexpr int SE_IMG = 4, SE_MAXC = 576, SE_MAXSQ = 144, SE_THREADS = 1024;
+// SE excitation: scale[b][c] = hardsigmoid( W2 relu(W1 mean + b1) + b2 )   (tv:ops/misc.py:243-261).
+// One thread-block CLUSTER of SE_CS CTAs per SE_IG images.  The two weight matrices (2 x 332 KB at C = 576) are what the layer
+// costs; a cluster reads each of them exactly once, one slice per CTA, so every SM pulls <= 1/8 of a matrix from L2 and the
+// whole chip works on one layer:
+//   phase 0  CTA r owns a channel slice (C/8 rounded up to whole quads): squeeze means of its channels (row partials added in order)
+//   phase 1  fc1 split along K: hid_r[img][j] = sum over the slice of mean[c] W1[c][j]  (W1 rows of the slice: one contiguous block)
+//   exchange cluster barrier; every CTA adds the 8 partials in rank order through distributed shared memory (+ b1, ReLU)
+//   phase 2  fc2 for the outputs of the slice: W2[:, slice] (+ b2, hardsigmoid) -> scale[img][slice]
+// All sums run in a fixed order that depends only on (C, SQ): the trunk stays bit-identical across batch sizes.
+// 9 launches took 178 us as one-CTA-per-4-images kernels (latency-bound: 64 CTAs, each streaming both matrices); this form is
+// bound by the cluster barrier and two short dependent load chains.
+constexpr int SE_CS = 8, SE_IG = 8, SE_THREADS = 256, SE_MAXC = 576, SE_MAXSQ = 144, SE_MAXSLICE = SE_MAXC / SE_CS, SE_MAXPARTS = 8;
+static_assert(SE_IG == 8, "the per-k image vectors are read as two float4");
 
-// out4[img] (valid in the lanes with slice 0) = sum_k v[k][img] * W[k][4g..4g+3]
-__device__ __forceinline__ bool se_fc_layer(const float* __restrict__ W, const float* v, int K, int N, float4 (&acc)[SE_IMG], int& g_out) {
-    const int G = N >> 2;
-    int S = 1;
-    while (S < 32 && G * (S * 2) <= SE_THREADS && S * 2 <= K) S *= 2;      // slices: power of two, adjacent lanes
-    const int tid = threadIdx.x, g = tid / S, sl = tid - g * S;
-    const bool active = g < G;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+
+__global__ void __cluster_dims__(SE_CS, 1, 1) __launch_bounds__(SE_THREADS)
+se_fc_kernel(const float* __restrict__ pool, int parts, const float* __restrict__ w1, const float* __restrict__ b1,
+             const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ scale, int B, int C, int SQ, float inv_hw) {
+    extern __shared__ __align__(16) float se_dyn[];            // W1 slice [cn][SQ] | W2 slice [SQ][cn]
+    __shared__ __align__(16) float m_s[SE_MAXSLICE][SE_IG];    // squeeze means of this CTA's channel slice, [channel][image]
+    __shared__ float part_s[SE_THREADS * SE_IG];               // per-thread-part partial sums of a phase
+    __shared__ float hp_s[SE_IG][SE_MAXSQ];                    // this CTA's fc1 partial (read by the whole cluster)
+    __shared__ __align__(16) float hid_s[SE_MAXSQ][SE_IG];     // full hidden layer, [unit][image]
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int tid = threadIdx.x;
+    const int b0 = (blockIdx.x / SE_CS) * SE_IG;
+    // slices are whole channel quads, so that both weight slices move as 16-byte copies (4-byte cp.async made the kernel L2-request bound)
+    const int slice = 4 * ((C + 4 * SE_CS - 1) / (4 * SE_CS)), c0 = (int)rank * slice, cn = max(0, min(slice, C - c0));
+    float* w1s = se_dyn; float* w2s = se_dyn + ((slice * SQ + 3) & ~3);
+    // ---- the CTA's two weight slices start towards shared memory right away: everything the layer reads is in flight at once
+    {
+        const int n4 = (cn * SQ) >> 2;                         // W1 rows of the slice are one contiguous block (SQ % 4 == 0: 16-byte copies)
+        const float* src = w1 + (size_t)c0 * SQ;
+        const uint32_t d1 = smem_u32_generic(w1s);
+        for (int i = tid; i < n4; i += SE_THREADS) cp_async16(d1 + 16u * i, src + 4 * i);
+        const uint32_t d2 = smem_u32_generic(w2s);
+        const int q4 = cn >> 2;
+        for (int i = tid; i < SQ * q4; i += SE_THREADS) { const int k = i / q4, c = (i - k * q4) << 2; cp_async16(d2 + 4u * (uint32_t)(k * cn + c), w2 + (size_t)k * C + c0 + c); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- phase 0: means of the slice (partials of an image's squeeze added top to bottom)
+    for (int i = tid; i < SE_IG * cn; i += SE_THREADS) {
+        const int img = i / cn, c = i - img * cn;
+        float sum = 0.f;
+        if (b0 + img < B) {
+            const float* pp = pool + (size_t)(b0 + img) * parts * C + c0 + c;
+            int t = 0;
+            for (; t + 8 <= parts; t += 8) {
+                float v[8];
 #pragma unroll
-    for (int i = 0; i < SE_IMG; i++) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        const float4* wp = reinterpret_cast<const float4*>(W) + g;
-#pragma unroll 8
-        for (int k = sl; k < K; k += S) {
-            const float4 w = __ldg(wp + (size_t)k * G);
-            const float4 x = *reinterpret_cast<const float4*>(v + k * SE_IMG);     // the SE_IMG images' k-th input
-            acc[0].x = fmaf(x.x, w.x, acc[0].x); acc[0].y = fmaf(x.x, w.y, acc[0].y); acc[0].z = fmaf(x.x, w.z, acc[0].z); acc[0].w = fmaf(x.x, w.w, acc[0].w);
-            acc[1].x = fmaf(x.y, w.x, acc[1].x); acc[1].y = fmaf(x.y, w.y, acc[1].y); acc[1].z = fmaf(x.y, w.z, acc[1].z); acc[1].w = fmaf(x.y, w.w, acc[1].w);
-            acc[2].x = fmaf(x.z, w.x, acc[2].x); acc[2].y = fmaf(x.z, w.y, acc[2].y); acc[2].z = fmaf(x.z, w.z, acc[2].z); acc[2].w = fmaf(x.z, w.w, acc[2].w);
-            acc[3].x = fmaf(x.w, w.x, acc[3].x); acc[3].y = fmaf(x.w, w.y, acc[3].y); acc[3].z = fmaf(x.w, w.z, acc[3].z); acc[3].w = fmaf(x.w, w.w, acc[3].w);
+                for (int u = 0; u < 8; u++) v[u] = __ldg(pp + (size_t)(t + u) * C);
+#pragma unroll
+                for (int u = 0; u < 8; u++) sum += v[u];
+            }
+            for (; t < parts; t++) sum += __ldg(pp + (size_t)t * C);
+        }
+        m_s[c][img] = sum * inv_hw;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // ---- phase 1: fc1 partial over the slice.  thread = (hidden unit j, part of the slice); parts are added in order
+    {
+        const int np = max(1, min(SE_MAXPARTS, SE_THREADS / SQ)), j = tid % SQ, pt = tid / SQ;
+        if (pt < np) {
+            float acc[SE_IG];
+#pragma unroll
+            for (int g = 0; g < SE_IG; g++) acc[g] = 0.f;
+            const int per = (cn + np - 1) / np, k0 = pt * per, k1 = min(cn, k0 + per);
+#pragma unroll 4
+            for (int k = k0; k < k1; k++) {
+                const float w = w1s[k * SQ + j];
+                const float4 ma = *reinterpret_cast<const float4*>(&m_s[k][0]), mb = *reinterpret_cast<const float4*>(&m_s[k][4]);
+                acc[0] = fmaf(ma.x, w, acc[0]); acc[1] = fmaf(ma.y, w, acc[1]); acc[2] = fmaf(ma.z, w, acc[2]); acc[3] = fmaf(ma.w, w, acc[3]);
+                acc[4] = fmaf(mb.x, w, acc[4]); acc[5] = fmaf(mb.y, w, acc[5]); acc[6] = fmaf(mb.z, w, acc[6]); acc[7] = fmaf(mb.w, w, acc[7]);
+            }
+#pragma unroll
+            for (int g = 0; g < SE_IG; g++) part_s[(pt * SE_IG + g) * SQ + j] = acc[g];
+        }
+        __syncthreads();
+        for (int i = tid; i < SE_IG * SQ; i += SE_THREADS) {
+            const int g = i / SQ, jj = i - g * SQ;
+            float h = 0.f;
+            for (int q = 0; q < np; q++) h += part_s[(q * SE_IG + g) * SQ + jj];
+            hp_s[g][jj] = h;
         }
     }
-    // S divides 32 and groups start at multiples of S, so a group's slices sit in one warp; idle lanes carry zeros
-    for (int o = S >> 1; o > 0; o >>= 1) {
+    // ---- exchange: all partials of the cluster are complete; add them in rank order
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    {
+        const uint32_t local = smem_u32_generic(&hp_s[0][0]);
+        for (int i = tid; i < SE_IG * SQ; i += SE_THREADS) {
+            const int g = i / SQ, jj = i - g * SQ;
+            const uint32_t off = local + (uint32_t)(g * SE_MAXSQ + jj) * 4u;
+            float v[SE_CS];
 #pragma unroll
-        for (int i = 0; i < SE_IMG; i++) {
-            acc[i].x += __shfl_xor_sync(0xffffffffu, acc[i].x, o); acc[i].y += __shfl_xor_sync(0xffffffffu, acc[i].y, o);
-            acc[i].z += __shfl_xor_sync(0xffffffffu, acc[i].z, o); acc[i].w += __shfl_xor_sync(0xffffffffu, acc[i].w, o);
+            for (int r = 0; r < SE_CS; r++) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(off), "r"(r));
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v[r]) : "r"(remote) : "memory");
+            }
+            float h = __ldg(b1 + jj);
+#pragma unroll
+            for (int r = 0; r < SE_CS; r++) h += v[r];
+            hid_s[jj][g] = fmaxf(h, 0.f);
         }
     }
-    g_out = g;
-    return active && sl == 0;
-}
-
-__global__ void __launch_bounds__(SE_THREADS) se_fc_kernel(const float* __restrict__ pool, int parts, const float* __restrict__ w1,
-                                                           const float* __restrict__ b1, const float* __restrict__ w2,
-                                                           const float* __restrict__ b2, float* __restrict__ scale,
-                                                           int B, int C, int SQ, float inv_hw) {
-    static_assert(SE_IMG == 4, "se_fc_layer reads the 4 images' inputs as one float4");
-    __shared__ __align__(16) float m[SE_MAXC * SE_IMG];       // [c][image]
-    __shared__ __align__(16) float hid[SE_MAXSQ * SE_IMG];    // [j][image]
-    const int b0 = blockIdx.x * SE_IMG, tid = threadIdx.x;
-    for (int i = tid; i < C * SE_IMG; i += SE_THREADS) {
-        const int img = i / C, c = i - img * C;
-        float sum = 0.f;                                      // per-tile partials of the squeeze, added in tile order
-        if (b0 + img < B)
-            for (int t = 0; t < parts; t++) sum += pool[((size_t)(b0 + img) * parts + t) * C + c];
-        m[c * SE_IMG + img] = sum * inv_hw;
-    }
-    __syncthreads();
-    float4 acc[SE_IMG]; int g;
-    if (se_fc_layer(w1, m, C, SQ, acc, g)) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(b1) + g);
-        const float a[4][4] = {{acc[0].x, acc[0].y, acc[0].z, acc[0].w}, {acc[1].x, acc[1].y, acc[1].z, acc[1].w},
-                               {acc[2].x, acc[2].y, acc[2].z, acc[2].w}, {acc[3].x, acc[3].y, acc[3].z, acc[3].w}};
-        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    // no CTA may exit (or overwrite hp_s) while a peer still reads its partial
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // ---- phase 2: fc2 + hardsigmoid for the channels of the slice.  thread = (channel, part of the hidden units)
+    if (cn > 0) {
+        const int np = max(1, min(SE_MAXPARTS, SE_THREADS / cn)), c = tid % cn, pt = tid / cn;
+        if (pt < np) {
+            float acc[SE_IG];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
+            for (int g = 0; g < SE_IG; g++) acc[g] = 0.f;
+            const int per = (SQ + np - 1) / np, k0 = pt * per, k1 = min(SQ, k0 + per);
+#pragma unroll 4
+            for (int k = k0; k < k1; k++) {
+                const float w = w2s[k * cn + c];
+                const float4 ha = *reinterpret_cast<const float4*>(&hid_s[k][0]), hb = *reinterpret_cast<const float4*>(&hid_s[k][4]);
+                acc[0] = fmaf(ha.x, w, acc[0]); acc[1] = fmaf(ha.y, w, acc[1]); acc[2] = fmaf(ha.z, w, acc[2]); acc[3] = fmaf(ha.w, w, acc[3]);
+                acc[4] = fmaf(hb.x, w, acc[4]); acc[5] = fmaf(hb.y, w, acc[5]); acc[6] = fmaf(hb.z, w, acc[6]); acc[7] = fmaf(hb.w, w, acc[7]);
+            }
 #pragma unroll
-            for (int img = 0; img < SE_IMG; img++) hid[(g * 4 + j) * SE_IMG + img] = fmaxf(a[img][j] + bb[j], 0.f);
-    }
-    __syncthreads();
-    if (se_fc_layer(w2, hid, SQ, C, acc, g)) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(b2) + g);
-#pragma unroll
-        for (int img = 0; img < SE_IMG; img++) {
-            if (b0 + img >= B) break;
-            float4 r;
-            r.x = apply_act(acc[img].x + bv.x, ACT_HSIGMOID); r.y = apply_act(acc[img].y + bv.y, ACT_HSIGMOID);
-            r.z = apply_act(acc[img].z + bv.z, ACT_HSIGMOID); r.w = apply_act(acc[img].w + bv.w, ACT_HSIGMOID);
-            reinterpret_cast<float4*>(scale + (size_t)(b0 + img) * C)[g] = r;
+            for (int g = 0; g < SE_IG; g++) part_s[(pt * SE_IG + g) * cn + c] = acc[g];
+        }
+        __syncthreads();
+        for (int i = tid; i < SE_IG * cn; i += SE_THREADS) {
+            const int g = i / cn, cc = i - g * cn;
+            if (b0 + g >= B) continue;
+            float a = __ldg(b2 + c0 + cc);
+            for (int q = 0; q < np; q++) a += part_s[(q * SE_IG + g) * cn + cc];
+            scale[(size_t)(b0 + g) * C + c0 + cc] = apply_act(a, ACT_HSIGMOID);
         }
     }
 }
 
 static int launch_se_fc(const MBBlock& m, const float* pool, int parts, float* scale, int B, float inv_hw, cudaStream_t s) {
-    if (m.exp > SE_MAXC || m.sq > SE_MAXSQ || (m.exp & 3) || (m.sq & 3)) { set_error("se_fc: unsupported SE shape %d -> %d", m.exp, m.sq); return KPD_ERR_UNSUPPORTED; }
-    se_fc_kernel<<<(B + SE_IMG - 1) / SE_IMG, SE_THREADS, 0, s>>>(pool, parts, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
+    if (m.exp > SE_MAXC || (m.exp & 3) || m.sq > SE_MAXSQ || m.sq < 4 || (m.sq & 3) || m.sq > SE_THREADS) { set_error("se_fc: unsupported SE shape %d -> %d", m.exp, m.sq); return KPD_ERR_UNSUPPORTED; }
+    const int clusters = (B + SE_IG - 1) / SE_IG;
+    const int slice = 4 * ((m.exp + 4 * SE_CS - 1) / (4 * SE_CS));
+    const size_t smem = sizeof(float) * (size_t)(((slice * m.sq + 3) & ~3) + slice * m.sq + 4);
+    static uint64_t attr = 0;
+    KPD_CUDA(ensure_smem_attr(se_fc_kernel, 100 * 1024, attr));
+    se_fc_kernel<<<clusters * SE_CS, SE_THREADS, smem, s>>>(pool, parts, m.w_fc1, m.b_fc1, m.w_fc2, m.b_fc2, scale, B, m.exp, m.sq, inv_hw);
     KPD_LAUNCH_CHECK();
     return 0;
 }

@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(F0_THREADS, 1)
 fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmL,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const Fpn0Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: shared-memory accesses must compile to LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * F0_STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);

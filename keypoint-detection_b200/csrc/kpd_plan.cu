@@ -3,6 +3,7 @@
 // (dll/models/keypoint_model.py:49-71, scripts/predict.py:47-57).
 #include "kpd_common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <math.h>
 #include <map>
@@ -19,22 +20,29 @@ void set_error(const char* fmt, ...) {
 
 // ---- optional CUDA-event profiling of tagged regions (bench roofline; off by default) ----
 struct ProfEntry { double ms = 0; int64_t n = 0; };
-static bool g_prof_on = false;
+// level 1: stage tags only ("body", "fpn0_conv", ...: one event pair per stage, the launches inside a stage stay back to back);
+// level 2: also the nested "stage.part" tags -- the extra events between the short trunk launches cost GPU idle time that lands
+// inside the enclosing stage's pair, so stage totals are read at level 1 and the breakdown at level 2.
+static int g_prof_on = 0;
 static std::map<std::string, ProfEntry> g_prof;
-struct Pending { std::string tag; cudaEvent_t a, b; };
+struct Pending { std::string tag; cudaEvent_t a, b; bool live; };
 static std::vector<Pending> g_pending;
 static std::vector<Pending> g_open;
 
 void prof_begin(const char* tag, cudaStream_t s) {
     if (!g_prof_on) return;
-    Pending p; p.tag = tag;
-    cudaEventCreate(&p.a); cudaEventCreate(&p.b);
-    cudaEventRecord(p.a, s);
+    Pending p; p.tag = tag; p.a = p.b = nullptr;
+    p.live = g_prof_on >= 2 || strchr(tag, '.') == nullptr;
+    if (p.live) {
+        cudaEventCreate(&p.a); cudaEventCreate(&p.b);
+        cudaEventRecord(p.a, s);
+    }
     g_open.push_back(p);
 }
 void prof_end(cudaStream_t s) {
     if (!g_prof_on || g_open.empty()) return;
     Pending p = g_open.back(); g_open.pop_back();
+    if (!p.live) return;
     cudaEventRecord(p.b, s);
     g_pending.push_back(p);
 }
@@ -174,7 +182,7 @@ using namespace kpd;
 extern "C" const char* kpd_last_error(void) { return kpd::g_err; }
 extern "C" int kpd_abi_version(void) { return KPD_ABI_VERSION; }
 extern "C" int64_t kpd_launch_count(int reset) { int64_t v = g_launches; if (reset) g_launches = 0; return v; }
-extern "C" int kpd_profile_enable(int on) { prof_collect(); g_prof_on = on != 0; if (on) g_prof.clear(); return 0; }
+extern "C" int kpd_profile_enable(int on) { prof_collect(); g_open.clear(); g_prof_on = on < 0 ? 0 : on; if (on) g_prof.clear(); return 0; }
 extern "C" int kpd_profile_read(const char* tag, double* total_ms, int64_t* launches) {
     prof_collect();
     auto it = g_prof.find(tag ? tag : "");

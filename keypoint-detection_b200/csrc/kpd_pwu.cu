@@ -39,13 +39,15 @@ struct PuHswish { __device__ __forceinline__ float operator()(float x) const { r
 __global__ void __launch_bounds__(PU_THREADS, 1)
 pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const PwUParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // (offset arithmetic on the __shared__ array, not an integer round trip: shared-memory accesses must compile to LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.stages;
     // stage: [A (raw fp32 from TMA, rewritten in place as A_hi) | A_lo | B_hi (Nc rows x 128 B) | B_lo]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_bytes);
     // bars: [0,S) full (TMA landed), [S,2S) split done, [2S,3S) free (MMAs retired), [3S,3S+2) tmem full, [3S+2,3S+4) tmem empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
-    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // [PU_MAXN] bias of every (padded) output column
+    // 16-byte aligned: stages are 1024-byte multiples, 3S+4 barriers of 8 bytes -> round the barrier block up to 16
+    float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((8 * (3 * S + 4) + 16 + 15) & ~15));   // [PU_MAXN] bias of every (padded) output column
     float* red = sbias + PU_MAXN;                              // [8 warps][32][PU_RS] transpose tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -31,7 +31,7 @@ for i in range(5):
     print(f"{'feat%d' % i if i < 4 else 'scores'}: max|strict| {float(a.abs().max()):.4g}  max abs diff {float((a - b).abs().max()):.3e}  rel-range {float((a - b).abs().max() / a.abs().max()):.3e}", flush=True)
 lib = _native.load()
 import ctypes as C
-lib.kpd_profile_enable(1)
+lib.kpd_profile_enable(2)
 for _ in range(5):
     m.predict({"image": x, "bboxes": boxes})
 torch.cuda.synchronize()
