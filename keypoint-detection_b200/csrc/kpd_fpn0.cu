@@ -33,7 +33,7 @@ struct Fpn0Params {
     int skip;                          // timing attribution only (KPD_FPN0_SKIP): 1 no part (A), 2 no part (B), 4 no output stores, 8 no pooling
 };
 
-constexpr int F0_EPI_WARPS = 8 /* 4 per tile of a group */, F0_RS = 36 /* padded row of the epilogue transpose tile */, F0_THREADS = 64 + 32 * F0_EPI_WARPS, F0_MT = 2, F0_SLOT = 16384, F0_STAGE = (F0_MT + 1) * F0_SLOT;
+constexpr int F0_EPI_WARPS = 8 /* 4 per tile of a group */, F0_CW = 16 /* channels per epilogue chunk */, F0_RS = F0_CW + 4 /* padded row of the epilogue transpose tile */, F0_THREADS = 64 + 32 * F0_EPI_WARPS, F0_MT = 2, F0_SLOT = 16384, F0_STAGE = (F0_MT + 1) * F0_SLOT;
 
 __device__ __forceinline__ int f0_first(int p) { return p == 0 ? -1 : 0; }            // first coarse-neighbour offset along an axis
 __device__ __forceinline__ int f0_count(int p) { return (p == 0 || p == 3) ? 2 : 1; }   // neighbours along an axis
@@ -48,7 +48,7 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * F0_STAGE);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
     float* sbias = reinterpret_cast<float*>(tmem_slot + 4);
-    float* red = sbias + 128;                          // [4 warps][32][F0_RS] transpose tiles (16-byte aligned rows)
+    float* red = sbias + 128;                          // [8 warps][32][F0_RS] transpose tiles (16-byte aligned rows)
     float* wred = red + F0_EPI_WARPS * 32 * F0_RS;        // [2 tiles][4 lane groups][2][128] channel sum / max over a lane group's 32 rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -205,14 +205,15 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
                 const int n_w = pair * 2 + (lg >> 1), cy_w = cyt * 4 + ((lg & 1) << 1);     // image / first coarse row of this warp's 32 rows
                 float* rt = red + (warp - 2) * (32 * F0_RS);
                 float* wr = wred + ti * (8 * 128);
-                // transposed read-back: lane = (row lane/8 of 4, 4 channels lane%8), 8 passes: a warp store = four 128-byte lines
-                const int rr4 = lane >> 3, q = lane & 7;
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    uint32_t r[32];
-                    tc_ld32(taddr + c0, r);
+                // transposed read-back: lane = (row lane/4 of 8, 4 channels lane%4), 4 passes: a warp store = eight 64-byte runs (full
+                // sectors).  16-channel chunks keep the transpose tiles at 20 KB, which buys the operand ring its fourth stage.
+                const int rr8 = lane >> 2, q = lane & 3;
+                for (int c0 = 0; c0 < 128; c0 += F0_CW) {
+                    uint32_t r[F0_CW];
+                    tc_ld16(taddr + c0, r);
                     tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
+                    for (int j = 0; j < F0_CW / 4; j++) {
                         float4 v;
                         v.x = fmaxf(__uint_as_float(r[4 * j + 0]) + sbias[c0 + 4 * j + 0], 0.f);     // folded BN shift + ReLU
                         v.y = fmaxf(__uint_as_float(r[4 * j + 1]) + sbias[c0 + 4 * j + 1], 0.f);
@@ -223,8 +224,8 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
                     __syncwarp();
                     float4 sm4 = make_float4(0.f, 0.f, 0.f, 0.f), mx4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int it = 0; it < 8; it++) {
-                        const int rr = it * 4 + rr4;                                         // tile row within this warp's 32
+                    for (int it = 0; it < 4; it++) {
+                        const int rr = it * 8 + rr8;                                         // tile row within this warp's 32
                         const int cx_r = cxt * 16 + (rr & 15), cy_r = cy_w + (rr >> 4);
                         const float4 x = *reinterpret_cast<const float4*>(rt + rr * F0_RS + 4 * q);
                         if (n_w < p.B && cx_r < p.Wc) {
@@ -237,13 +238,13 @@ fpn0_fused_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_constant
                         }
                     }
 #pragma unroll
-                    for (int o = 8; o <= 16; o <<= 1) {                                      // combine the 4 row groups (lanes q, q+8, q+16, q+24)
+                    for (int o = 4; o <= 16; o <<= 1) {                                      // combine the 8 row groups (lanes q, q+4, ..., q+28)
                         sm4.x += __shfl_xor_sync(0xffffffffu, sm4.x, o); sm4.y += __shfl_xor_sync(0xffffffffu, sm4.y, o);
                         sm4.z += __shfl_xor_sync(0xffffffffu, sm4.z, o); sm4.w += __shfl_xor_sync(0xffffffffu, sm4.w, o);
                         mx4.x = fmaxf(mx4.x, __shfl_xor_sync(0xffffffffu, mx4.x, o)); mx4.y = fmaxf(mx4.y, __shfl_xor_sync(0xffffffffu, mx4.y, o));
                         mx4.z = fmaxf(mx4.z, __shfl_xor_sync(0xffffffffu, mx4.z, o)); mx4.w = fmaxf(mx4.w, __shfl_xor_sync(0xffffffffu, mx4.w, o));
                     }
-                    if (lane < 8) {
+                    if (lane < 4) {
                         *reinterpret_cast<float4*>(wr + (lg * 2 + 0) * 128 + c0 + 4 * q) = sm4;
                         *reinterpret_cast<float4*>(wr + (lg * 2 + 1) * 128 + c0 + 4 * q) = mx4;
                     }

@@ -16,8 +16,12 @@ int pointwise_gemm(const PwMma& p, int sm_count, cudaStream_t s) {
     static const bool force_umma = getenv("KPD_PW_UMMA") != nullptr;
     static const bool force_ffma = getenv("KPD_PW_FFMA") != nullptr;
     if (p.Wu && !p.exact && !force_ffma) {
-        const bool prefer_ffma = (p.K <= 16) || (p.N <= 24 && p.res) || (p.res && p.res_mode == 2 && p.K <= 24);
-        if (force_umma || !prefer_ffma) return pointwise_umma(p, sm_count, s);
+        // (the tcgen05 kernel stages the SE factors of a tile's images in shared memory: maps of < 32 pixels -- inputs below 160 x 160 --
+        //  would need more than its 4 x 576 floats)
+        const int hw = p.hw > 0 ? p.hw : 1;
+        const bool se_fits = !p.se_scale || (int64_t)((127 + hw - 1) / hw + 1) * p.K <= 4 * 576;
+        const bool prefer_ffma = (p.K <= 16) || (p.N <= 24 && p.res) || (p.res && p.res_mode == 2 && p.K <= 24) || !se_fits;
+        if ((force_umma && se_fits) || !prefer_ffma) return pointwise_umma(p, sm_count, s);
     }
     if (!p.Wraw) { set_error("pointwise_gemm: missing weights"); return KPD_ERR_ARG; }
     return pointwise_ffma(p, sm_count, s);

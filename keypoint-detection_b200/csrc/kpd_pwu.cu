@@ -28,6 +28,7 @@ struct PwUParams {
 };
 
 constexpr int PU_EPI_WARPS = 8, PU_THREADS = 192 + 32 * PU_EPI_WARPS, PU_RS = 36, PU_MAXN = 640;
+constexpr int PU_SC_FLOATS = 4 * 576;                         // SE factors staged per tile: (images a 128-row tile can span) x K floats
 constexpr int PU_A = 16384;                                   // one 128 x 32-float slab
 
 template <typename ActFn>
@@ -49,6 +50,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 16-byte aligned: stages are 1024-byte multiples, 3S+4 barriers of 8 bytes -> round the barrier block up to 16
     float* sbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((8 * (3 * S + 4) + 16 + 15) & ~15));   // [PU_MAXN] bias of every (padded) output column
     float* red = sbias + PU_MAXN;                              // [8 warps][32][PU_RS] transpose tiles
+    float* sscale = red + PU_EPI_WARPS * 32 * PU_RS;            // [PU_SC_IMGS][K] SE excitation factors of the current tile's images
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
@@ -127,31 +129,38 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
             const int tm = item / p.nchunks;
             const uint32_t m0 = (uint32_t)tm * 128u;
-            uint32_t img[8];
+            // SE excitation factors of the tile's images: staged once per item ([image][K], the images of a tile are consecutive, so
+            // it is one contiguous block) -- as per-slab global loads they doubled the kernel's L2 requests and put an L2 round trip
+            // into every slab of the serial split stage
+            const float* srow[8];
             if (p.se_scale) {
+                const uint32_t img0 = m0 / (uint32_t)p.hw, img1 = min(m0 + 127u, p.M - 1) / (uint32_t)p.hw;
+                const int nv = (int)(img1 - img0 + 1) * (p.K >> 2);
+                asm volatile("bar.sync 2, 128;" ::: "memory");                   // every split thread is done with the previous item's factors
+                const float4* src = reinterpret_cast<const float4*>(p.se_scale + (size_t)img0 * p.K);
+                for (int i = t; i < nv; i += 128) reinterpret_cast<float4*>(sscale)[i] = __ldg(src + i);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 8; i++) img[i] = min(m0 + (uint32_t)((t >> 3) + 16 * i), p.M - 1) / (uint32_t)p.hw;
+                for (int i = 0; i < 8; i++) srow[i] = sscale + (size_t)(min(m0 + (uint32_t)((t >> 3) + 16 * i), p.M - 1) / (uint32_t)p.hw - img0) * p.K;
             }
             for (int sl = 0; sl < nslabs; sl++) {
-                // SE excitation factors of this slab's chunks: loaded before the wait, so their L2 latency hides behind the TMA's
-                float4 sc[8];
-                if (p.se_scale) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int f = t + 128 * i, row = f >> 3, k = sl * 32 + (((f & 7) ^ (row & 7)) << 2);
-                        sc[i] = k < p.K ? __ldg(reinterpret_cast<const float4*>(p.se_scale + (size_t)img[i] * p.K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
                 mbar_wait(full_bar(stage), phase);
                 uint8_t* sp = smem + (size_t)stage * p.stage_bytes;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int f = t + 128 * i;                                   // float4 index: row f >> 3, stored chunk position f & 7
                     float4 a = *reinterpret_cast<const float4*>(sp + f * 16);
-                    if (p.se_scale) { a.x *= sc[i].x; a.y *= sc[i].y; a.z *= sc[i].z; a.w *= sc[i].w; }
+                    if (p.se_scale) {
+                        const int row = f >> 3, k = sl * 32 + (((f & 7) ^ (row & 7)) << 2);      // 128-byte swizzle: chunk position -> k
+                        const float4 sc = k < p.K ? *reinterpret_cast<const float4*>(srow[i] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        a.x *= sc.x; a.y *= sc.y; a.z *= sc.z; a.w *= sc.w;
+                    }
+                    // x = hi + lo: hi = x with the 13 low mantissa bits cleared (what the tensor core reads of an fp32 operand), lo = x - hi
+                    // (exact; the tensor core truncates it to tf32 itself): |x - hi - tf32(lo)| <= 2^-20 |x| for one LOP3 + one FADD per element
                     float4 hi, lo;
-                    hi.x = tf32_rna(a.x); hi.y = tf32_rna(a.y); hi.z = tf32_rna(a.z); hi.w = tf32_rna(a.w);
-                    lo.x = tf32_rna(a.x - hi.x); lo.y = tf32_rna(a.y - hi.y); lo.z = tf32_rna(a.z - hi.z); lo.w = tf32_rna(a.w - hi.w);
+                    hi.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+                    hi.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+                    lo.x = a.x - hi.x; lo.y = a.y - hi.y; lo.z = a.z - hi.z; lo.w = a.w - hi.w;
                     *reinterpret_cast<float4*>(sp + f * 16) = hi;                  // in place: same thread, same 16 bytes
                     *reinterpret_cast<float4*>(sp + PU_A + f * 16) = lo;
                 }
@@ -275,7 +284,8 @@ int pointwise_umma(const PwMma& a, int sm_count, cudaStream_t s) {
     p.out2 = a.out2; p.split = a.split; p.n2 = a.n2;
     p.act = a.act; p.hw = a.hw > 0 ? a.hw : 1; p.res_mode = a.res ? a.res_mode : 0; p.H = a.H; p.W = a.W; p.up = a.up > 0 ? a.up : 1; p.round_tf32 = a.round_tf32;
     p.stage_bytes = 2 * PU_A + 2 * p.Nc * 128;
-    const int misc = 1024 /*align*/ + 8 * (3 * 8 + 4) + 32 + 4 * PU_MAXN + 4 * (PU_EPI_WARPS * 32 * PU_RS) + 64;
+    const int misc = 1024 /*align*/ + 8 * (3 * 8 + 4) + 32 + 4 * PU_MAXN + 4 * (PU_EPI_WARPS * 32 * PU_RS) + 4 * PU_SC_FLOATS + 64;
+    if (a.se_scale && (int64_t)((127 + p.hw - 1) / p.hw + 1) * a.K > PU_SC_FLOATS) { set_error("pointwise_umma: SE factors of a tile (%d px/image, K = %d) exceed the staging buffer", p.hw, a.K); return KPD_ERR_UNSUPPORTED; }
     if (p.Np > PU_MAXN) { set_error("pointwise_umma: N = %d too wide", a.N); return KPD_ERR_UNSUPPORTED; }
     int stages = (227 * 1024 - misc) / p.stage_bytes; if (stages > 6) stages = 6;
     if (stages < 2) { set_error("pointwise_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
