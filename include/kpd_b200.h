@@ -164,6 +164,19 @@ int  kpd_box_iou(const float* d_boxes1, int n1, const float* d_boxes2, int n2, f
 int  kpd_nms(const float* d_boxes, const float* d_scores, int batch, int m, float iou_thr, int max_out,
              int32_t* d_keep, int32_t* d_keep_count, void* stream);
 
+/* NEW BEHAVIOUR, no reference semantics (the reference's bare-tensor forward crashes: keypoint_model.py:114-119 ->
+ * person_head.py:141-166 returns raw head outputs): person boxes from the level-0 heads.
+ * d_box [B,H*W,36] / d_cls [B,H*W,9] = kpd_person_heads outputs on the FPN-0 map of `size` x `size` images.  Per image:
+ * 9 anchors per pixel in the order of person_head.py:45-51 (sizes anchor_sizes3[0..2] x ratios 0.5,1,2; normalised by `size`),
+ * standard delta decode, score = sigmoid(logit); the top_m (<= 128) candidates by score, those >= conf_threshold, greedy NMS
+ * (kpd_nms) at iou_threshold; the first max_persons survivors in descending score order -> d_boxes_out [B,max_persons,4]
+ * normalised cx,cy,w,h, zero-padded (all-zero box = padding, keypoint_model.py:149); d_count int32 [B] (may be NULL).
+ * d_scratch: kpd_detect_scratch_bytes(batch, top_m) bytes, 16-byte aligned. */
+int  kpd_detect_persons(const float* d_box, const float* d_cls, int batch, int height, int width, int size,
+                        const float* anchor_sizes3, float conf_threshold, float iou_threshold, int top_m, int max_persons,
+                        float* d_boxes_out, int32_t* d_count, void* d_scratch, void* stream);
+size_t kpd_detect_scratch_bytes(int batch, int top_m);
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* kpd_last_error(void);
 int  kpd_abi_version(void);

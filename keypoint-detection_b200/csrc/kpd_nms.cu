@@ -75,6 +75,14 @@ __global__ void __launch_bounds__(256) nms_kernel(const float* __restrict__ boxe
     if (tid == 0) keep_count[img] = kept;
 }
 
+// in-library launch (kpd_detect.cu)
+int nms_launch(const float* boxes, const float* scores, int batch, int m, float iou_thr, int max_out, int32_t* keep, int32_t* keep_count, cudaStream_t s) {
+    if (m > NMS_MAX) { set_error("nms: at most %d candidates per image (got %d)", NMS_MAX, m); return KPD_ERR_ARG; }
+    nms_kernel<<<batch, 256, 0, s>>>(boxes, scores, m, iou_thr, max_out, keep, keep_count);
+    KPD_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace kpd
 
 using namespace kpd;

@@ -58,6 +58,9 @@ _SIGNATURES = {
     "kpd_person_heads": (C.c_int, [_P, C.c_int, _P, C.c_int64, _P, _P, _P]),
     "kpd_box_iou": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P]),
     "kpd_nms": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, _P]),
+    "kpd_detect_persons": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float,
+                                     C.c_int, C.c_int, _P, _P, _P, _P]),
+    "kpd_detect_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "kpd_last_error": (C.c_char_p, []),
     "kpd_abi_version": (C.c_int, []),
     "kpd_launch_count": (C.c_int64, [C.c_int]),

@@ -146,9 +146,11 @@ class MultiPersonKeypointModel(nn.Module):
             else:
                 boxes = torch.zeros(batch_size, 0, 4, device=dev)
         else:
-            # upstream routes this case to PERSON_HEAD.forward, which fails with a channel mismatch
-            # (SURVEY.md 0.5); there is no reference behaviour to reproduce.
-            raise NotImplementedError("forward() needs batch['bboxes']: the person-detector path has no reference semantics")
+            # Upstream routes this case to PERSON_HEAD.forward, which returns raw head outputs and then fails with a channel
+            # mismatch (keypoint_model.py:114-119): there is no reference behaviour to reproduce.  NEW behaviour,
+            # defined in csrc/kpd_detect.cu: boxes from the level-0 person heads on FPN-0 (anchor decode, top-100, confidence
+            # threshold, NMS), padded to `max_detections` slots with all-zero boxes.
+            return self._forward_detect(x, plan, dev)
         if boxes.size(-1) != 4:
             raise ValueError(f"Invalid bboxes format: {boxes.shape}")
         person_bboxes = list(boxes.unbind(0))          # per-image box tensors, as the reference returns them (one op, not B slices)
@@ -211,6 +213,47 @@ class MultiPersonKeypointModel(nn.Module):
                 for i in range(nchunks):
                     cur.wait_stream(self._chunk_streams[i])
         return {'heatmap': heat, 'keypoints': kpts, 'visibilities': vis, 'boxes': person_bboxes}
+
+    max_detections = 4       # person slots of the detector path (fixed, so that no host synchronisation is needed)
+    detect_top_m = 100       # candidates per image entering NMS ("<= 100 candidates per image")
+
+    def _forward_detect(self, x, plan, dev):
+        """Bare-tensor forward (NEW behaviour, see kpd_detect.cu): trunk + FPN-0 -> person heads -> kpd_detect_persons ->
+        the same ROI / head / decode stages as the box path.  Output dict as forward(); 'boxes' holds the detected boxes
+        [P,4] per image (all-zero rows = empty slots)."""
+        lib = N.load()
+        B, S, K, P = x.size(0), x.size(2), self.num_keypoints, self.max_detections
+        prec = N.PRECISIONS[self.precision]
+        det = self.person_detector
+        with torch.cuda.device(dev):
+            xd = as_cuda_f32(x, dev)
+            L = plan.layout(B, S, B * P, prec)
+            ws = self._workspace.get(L.total_bytes, dev)
+            st = N.stream_ptr(dev)
+            N.check(lib.kpd_backbone_fpn0(plan.handle, prec, N.ptr(xd), B, S, N.ptr(ws), L, st), "kpd_backbone_fpn0")
+            N.check(lib.kpd_channel_topk(plan.handle, B, N.ptr(ws), L, st), "kpd_channel_topk")
+            h0 = S // 2
+            pixels = B * h0 * h0
+            fpn0 = stage_views(ws, L, B, S, 0, prec)["fpn0"]
+            box = torch.empty(pixels, 36, device=dev, dtype=torch.float32)
+            cls = torch.empty(pixels, 9, device=dev, dtype=torch.float32)
+            N.check(lib.kpd_person_heads(plan.handle, 0, N.ptr(fpn0), pixels, N.ptr(box), N.ptr(cls), st), "kpd_person_heads")
+            boxes = torch.empty(B, P, 4, device=dev, dtype=torch.float32)
+            count = torch.empty(B, device=dev, dtype=torch.int32)
+            scratch = torch.empty(int(lib.kpd_detect_scratch_bytes(B, self.detect_top_m)), device=dev, dtype=torch.uint8)
+            import ctypes as C
+            sizes = (C.c_float * 3)(*[float(v) for v in det.anchor_sizes])
+            N.check(lib.kpd_detect_persons(N.ptr(box), N.ptr(cls), B, h0, h0, S, sizes, float(det.conf_threshold),
+                                           float(det.nms_iou_threshold), self.detect_top_m, P, N.ptr(boxes), N.ptr(count),
+                                           N.ptr(scratch), st), "kpd_detect_persons")
+            heat = torch.empty(B, P, K, 56, 56, device=dev, dtype=torch.float32)
+            kpts = torch.empty(B, P, 1, K, 2, device=dev, dtype=torch.float32)
+            vis = torch.empty(B, P, 1, K, 3, device=dev, dtype=torch.float32)
+            N.check(lib.kpd_roi_head(plan.handle, prec, B, S, N.ptr(boxes), P, None, N.ptr(heat), N.ptr(kpts), N.ptr(vis),
+                                     N.ptr(ws), L, st), "kpd_roi_head")
+            self._last = (ws, L, B, S, B * P, prec)
+            self._last_detect = {"box": box.view(B, h0 * h0, 36), "cls": cls.view(B, h0 * h0, 9), "count": count}
+        return {'heatmap': heat, 'keypoints': kpts, 'visibilities': vis, 'boxes': list(boxes.unbind(0))}
 
     @torch.no_grad()
     def predict(self, batch, **kw):

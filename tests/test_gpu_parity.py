@@ -243,8 +243,6 @@ def test_error_behaviour(model):
         model.predict({"image": x, "bboxes": torch.zeros(1, 4)})
     with pytest.raises(ValueError):
         model.predict({"image": x, "bboxes": [torch.zeros(4)]})
-    with pytest.raises(NotImplementedError):
-        model.predict(x)
     model.train()
     with pytest.raises(RuntimeError):
         model.forward({"image": x, "bboxes": torch.zeros(1, 1, 4)})
@@ -595,3 +593,39 @@ def test_stock_weights_batch8(mode, tol):
     x = torch.from_numpy(synth_images(8, 1, 224, seed=99))
     boxes = torch.from_numpy(synth_boxes(8, 3, seed=7, zero_slots=((2, 1),)))
     _compare_selected_with_oracle(m, sd, x, boxes, list(range(8)), mode, tol, True, f"stock_b8/{mode}")
+
+
+def test_detector_path_new_semantics(model, sd):
+    """Bare-tensor forward.  NEW behaviour without a reference (upstream crashes there): the boxes must be
+    exactly what oracle.detect derives from the GPU's own head outputs, and the keypoint stages must give what the box path
+    gives for those boxes."""
+    from oracle.detect import detect_persons
+    B, S = 3, 224
+    x = torch.from_numpy(synth_images(B, 1, S, seed=321)).cuda()
+    model.set_precision("fp32")
+    det = model.person_detector
+    out = model.predict(x)
+    torch.cuda.synchronize()
+    P = model.max_detections
+    assert out["heatmap"].shape == (B, P, 17, 56, 56) and out["keypoints"].shape == (B, P, 1, 17, 2) and out["visibilities"].shape == (B, P, 1, 17, 3)
+    boxes = torch.stack(out["boxes"]).cpu().numpy()
+    dbg = model._last_detect
+    ref_boxes, ref_count = detect_persons(dbg["box"].cpu().numpy(), dbg["cls"].cpu().numpy(), S // 2, S // 2, S, tuple(det.anchor_sizes),
+                                          det.conf_threshold, det.nms_iou_threshold, model.detect_top_m, P)
+    assert np.array_equal(dbg["count"].cpu().numpy(), ref_count), (dbg["count"].cpu().numpy(), ref_count)
+    assert ref_count.max() >= 1
+    np.testing.assert_allclose(boxes, ref_boxes, rtol=0, atol=2e-6)
+    # the same boxes through the box path: identical keypoint stages (same kernels, same inputs)
+    again = model.predict({"image": x, "bboxes": torch.from_numpy(boxes).cuda()})
+    assert torch.equal(again["heatmap"], out["heatmap"]) and torch.equal(again["keypoints"], out["keypoints"])
+    assert torch.equal(again["visibilities"], out["visibilities"])
+    # nothing passes the confidence threshold -> all-zero boxes -> the reference's dummy person per image (keypoint_model.py:171-179)
+    old = det.conf_threshold
+    try:
+        det.conf_threshold = 1.1
+        none = model.predict(x)
+        assert float(torch.stack(none["boxes"]).abs().max()) == 0.0
+        assert float(none["heatmap"].abs().max()) == 0.0
+        assert torch.equal(none["visibilities"][:, 0, 0].cpu(), torch.tensor([[1.0, 0.0, 0.0]]).repeat(B, 17, 1))
+    finally:
+        det.conf_threshold = old

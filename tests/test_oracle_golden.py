@@ -146,3 +146,20 @@ def test_person_heads_match_reference(sd):
     box, cls = OM.person_heads(sd, torch.from_numpy(g["x"]))
     np.testing.assert_allclose(box.numpy(), g["box"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(cls.numpy(), g["cls"], rtol=1e-5, atol=1e-6)
+
+
+def test_detect_restatement_properties():
+    """oracle.detect states NEW semantics (no reference exists for the bare-tensor path): check its defining properties."""
+    from oracle.detect import detect_persons
+    H = W = 8; S = 16
+    rng = np.random.default_rng(5)
+    box = (0.1 * rng.standard_normal((2, H * W, 36))).astype(np.float32)
+    cls = (-4 + 0.1 * rng.standard_normal((2, H * W, 9))).astype(np.float32)      # everything below the confidence threshold ...
+    cls[0, 3 * W + 4, 4] = 5.0; cls[0, 3 * W + 4, 5] = 4.0                          # ... except two overlapping anchors of one pixel
+    cls[0, 6 * W + 1, 1] = 3.0                                                      # and one far away
+    boxes, count = detect_persons(box, cls, H, W, S, (2, 4, 8), 0.3, 0.3, 100, 4)
+    assert count.tolist() == [2, 0] and boxes.shape == (2, 4, 4)
+    assert np.all(boxes[1] == 0) and np.all(boxes[0, 2:] == 0)
+    # best candidate first: pixel (3,4), anchor 4 = size 4, ratio 1 -> centre near (4.5/8, 3.5/8), side near 4/16
+    assert abs(boxes[0, 0, 0] - 4.5 / 8) < 0.05 and abs(boxes[0, 0, 1] - 3.5 / 8) < 0.05 and abs(boxes[0, 0, 2] - 0.25) < 0.05
+    assert abs(boxes[0, 1, 0] - 1.5 / 8) < 0.08 and abs(boxes[0, 1, 1] - 6.5 / 8) < 0.08      # the overlapping second anchor was suppressed
