@@ -373,14 +373,13 @@ static int run_body_batched(const kpd_plan* p, const float* images, int B, int S
     }
     const float* cur = feat[0];
     int H = S / 2;
-    static const bool no_ed = getenv("KPD_NO_ED") != nullptr;      // A/B timing: the layer-by-layer expand GEMM + depthwise kernels
     for (int i = 0; i < 11; i++) {
         const MBBlock& m = p->blocks[i];
         const int Ho = H / m.stride;
         const float* x = cur;
         int pool_parts = 1;
         bool fused = false;
-        if (m.w_exp && !strict_fp32 && !no_ed) {
+        if (m.w_exp && !strict_fp32) {
             // expand + depthwise (+ squeeze partials) in one kernel, the expanded tensor stays on chip (kpd_ed.cu); layers whose
             // bands do not fit an SM (wide maps of large inputs) fall through to the two-kernel form below
             ProfScope ps("body.expand_dw", s);

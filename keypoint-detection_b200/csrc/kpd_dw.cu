@@ -207,8 +207,7 @@ int depthwise_tma(const MBBlock& m, const float* in, float* out, float* pool, si
     if ((C & 3) || (K != 3 && K != 5) || (S != 1 && S != 2) || (m.act != ACT_RELU && m.act != ACT_HSWISH) || (int64_t)Ho * Ho * C >= ((int64_t)1 << 31)) { set_error("depthwise_tma: unsupported layer C=%d k=%d stride=%d", C, K, S); return KPD_ERR_UNSUPPORTED; }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return KPD_ERR_STATE; }
-    static const int tile_kb = getenv("KPD_DW_TILE_KB") ? atoi(getenv("KPD_DW_TILE_KB")) : 48;
-    static const int stages_env = getenv("KPD_DW_STAGES") ? atoi(getenv("KPD_DW_STAGES")) : 2;
+    constexpr int tile_kb = 48, stages_env = 2;             // tile budget per stage (KB) and ring depth: the measured best
     static std::mutex mu;
     static std::map<std::tuple<int, int, int, int>, DwCfg> cache;
     DwCfg cfg;

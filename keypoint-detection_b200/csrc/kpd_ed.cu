@@ -12,7 +12,7 @@
 //                   and one parameter block (expand bias, depthwise bias, k*k tap rows) into a 3-deep ring
 //   split warps   : raw -> tf32 hi (in place) + lo (x = hi + lo to ~2^-21: the 3xTF32 scheme of kpd_pwu.cu)
 //   MMA thread    : per chunk and M-tile 3 x ceil(K/8) tcgen05.mma (kind::tf32, N = 32) into a double-buffered TMEM accumulator
-//   compute warps : (16 warps) tcgen05.ld -> +bias, activation -> the chunk's expanded tile in shared memory
+//   compute warps : (8 warps) tcgen05.ld -> +bias, activation -> the chunk's expanded tile in shared memory
 //                   [image][row + halo][col + halo][32 ch + 4 pad], zero where the depthwise conv pads -> depthwise conv with a
 //                   lane per channel and a k-row register window (the inner loop of kpd_dw.cu) -> coalesced 128-byte stores of
 //                   the block's depthwise output, per-(image, output row) squeeze partials in a canonical order
@@ -38,8 +38,16 @@ namespace kpd {
 
 constexpr int ED_CW = 32;            // expanded channels per chunk (= N of one MMA)
 constexpr int ED_ES = 36;            // floats per pixel of the expanded tile: 32 + 4 padding => conflict-free row stores and lane = channel loads
-constexpr int ED_CWARPS = 16, ED_CTHREADS = 32 * ED_CWARPS;   // compute warps: four per SM sub-partition hide each other's latencies
-constexpr int ED_THREADS = 192 + ED_CTHREADS;                 // 22 warps: TMA, MMA, 4 split, 16 compute
+// Eight compute warps (two per SM sub-partition) measured faster than sixteen (0.86 vs 0.96 ms over the ten layers): the phase is
+// bound by instruction issue and per-chunk hand-offs, not by latency hiding, and at <= 146 registers per thread the 5x5 window loop
+// neither spills nor needs the narrow 2-column form.  (-DKPD_ED_CWARPS=16 rebuilds the old shape for A/B runs.)
+#ifndef KPD_ED_CWARPS
+#define KPD_ED_CWARPS 8
+#endif
+constexpr int ED_CWARPS = KPD_ED_CWARPS, ED_CTHREADS = 32 * ED_CWARPS, ED_EC = 32 / (ED_CWARPS / 4);   // ED_EC: chunk columns a compute warp drains
+static_assert(ED_CWARPS == 8 || ED_CWARPS == 16, "compute warps: 2 or 4 per TMEM lane group");
+constexpr int ED_CTHREADS_ = ED_CTHREADS;   // compute warps: four per SM sub-partition hide each other's latencies
+constexpr int ED_THREADS = 192 + ED_CTHREADS;                 // 14 warps: TMA, MMA, 4 split, 8 compute
 constexpr int ED_MAXT = 8, ED_MAXG = 8, ED_MAXBST = 4;
 
 struct EdParams {
@@ -72,10 +80,15 @@ __device__ __forceinline__ void ed_wait(uint32_t bar, uint32_t parity) {
 
 #define ED_TRACE(role, ev) do { if (p.trace && blockIdx.x == 0 && (ev) < 256) p.trace[(role) * 256 + (ev)] = clock64(); } while (0)
 
-// output columns per depthwise work unit: 4 for the 3x3 layers, 2 for the 5x5 ones -- the unrolled window loop of a 5x5 layer
-// at 4 columns is ~20 KB of code (100 FMAs per row x the ring period), which made the compute warps instruction-fetch bound;
-// at 2 columns it is ~6 KB and the 25 + 30 window / weight registers leave room for 16 compute warps
-__host__ __device__ constexpr int ed_xr(int K, int S) { return K == 5 ? 2 : 4; }
+// output columns per depthwise work unit: 4 (measured: 2 and 3 columns for the 5x5 layers and 7 columns for either kernel size are
+// slower -- 7 spills the 5x5 window, 2 doubles the per-unit set-up)
+#ifndef KPD_ED_XR5
+#define KPD_ED_XR5 4
+#endif
+#ifndef KPD_ED_XR3
+#define KPD_ED_XR3 4
+#endif
+__host__ __device__ constexpr int ed_xr(int K, int S) { return K == 5 ? KPD_ED_XR5 : KPD_ED_XR3; }
 
 template <int KS, int S, bool HSW>       // HSW: hardswish (else ReLU) after the expand and the depthwise conv
 __global__ void __launch_bounds__(ED_THREADS, 1)
@@ -327,9 +340,9 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 float w[KK];
 #pragma unroll
                 for (int t = 0; t < KK; t++) w[t] = par[(2 + t) * ED_CW + lane];
-                float4 be[2];
+                float4 be[ED_EC / 4];
 #pragma unroll
-                for (int j = 0; j < 2; j++) be[j] = *reinterpret_cast<const float4*>(par + cpart * 8 + 4 * j);
+                for (int j = 0; j < ED_EC / 4; j++) be[j] = *reinterpret_cast<const float4*>(par + cpart * ED_EC + 4 * j);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(b_empty(s));      // the chunk's parameters are in registers
                 mbar_wait_warp(acc_full(a), aph, lane);
@@ -340,13 +353,14 @@ ed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                 for (int t = 0; t < ED_MAXT; t++) {
                     if (t < Tit) {
-                        uint32_t r[8];
-                        tc_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((a * p.T + t) * ED_CW + cpart * 8), r);
+                        uint32_t r[ED_EC];
+                        if constexpr (ED_EC == 8) tc_ld8(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((a * p.T + t) * ED_CW + cpart * ED_EC), r);
+                        else tc_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((a * p.T + t) * ED_CW + cpart * ED_EC), r);
                         tc_wait_ld();
                         if (eoff[t] >= 0) {
-                            float* dst = eb + eoff[t] + cpart * 8;
+                            float* dst = eb + eoff[t] + cpart * ED_EC;
 #pragma unroll
-                            for (int j = 0; j < 2; j++) {
+                            for (int j = 0; j < ED_EC / 4; j++) {
                                 float4 v;
                                 v.x = __uint_as_float(r[4 * j + 0]) + be[j].x; v.y = __uint_as_float(r[4 * j + 1]) + be[j].y;
                                 v.z = __uint_as_float(r[4 * j + 2]) + be[j].z; v.w = __uint_as_float(r[4 * j + 3]) + be[j].w;

@@ -283,10 +283,9 @@ __global__ void __launch_bounds__(256) roi_align_sep_kernel(const float* __restr
 
 static int launch_roi_align(const float* fpn0, const int32_t* topk, const float* roi_box, const int32_t* roi_batch, const int32_t* roi_count,
                             float* roi_feat, float* part, int n, int H, int W, cudaStream_t s) {
-    static const bool legacy = getenv("KPD_ROI_SAMPLEWISE") != nullptr;      // sample-by-sample form, kept for A/B checks
     const size_t dyn = sizeof(float) * (size_t)W * 64;
     const int gmax = std::max((H + 55) / 56, (W + 55) / 56);
-    if (!legacy && gmax <= RA_MAXG && dyn <= 160 * 1024) {
+    if (gmax <= RA_MAXG && dyn <= 160 * 1024) {       // else (maps beyond 392 pixels a side): the sample-by-sample kernel
         static uint64_t attr4 = 0, attr8 = 0;
         if (gmax + 1 <= 4) {
             KPD_CUDA(ensure_smem_attr(roi_align_sep_kernel<4>, 160 * 1024, attr4));    // set once per device: the maximum any call may ask for

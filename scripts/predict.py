@@ -2,7 +2,7 @@
 """Keypoint prediction CLI on the B200-native `dll` drop-in (reference: scripts/predict.py:30-226).
 
     python scripts/predict.py --config configs/default_config.yaml --model ckpt.pth --input image_or_dir \
-        [--gt label_file_or_dir] --output out_dir [--device cuda] [--precision bf16|fp32|fp32_strict] [--full-image-box]
+        [--gt label_file_or_dir] --output out_dir [--device cuda] [--precision bf16|fp32|fp32_strict] [--full-image-box | --detect]
 
 Same command line, checkpoint handling and printout as the reference's script:
   * the checkpoint is either a training checkpoint {'epoch','model_state_dict','optimizer_state_dict','history'} (keys the
@@ -14,7 +14,8 @@ The reference imports two modules that do not exist upstream (dll.data.create_da
 dll.data.dataloader.visualize_keypoints_multi_person are importable only with matplotlib present) and writes no
 output file although it logs one; here every image additionally gets `<stem>_keypoints.json` in --output.
 Without a label file the reference passes bboxes=None and returns all-zero keypoints; --full-image-box substitutes the
-box [0.5, 0.5, 1, 1] instead (new behaviour, off by default).
+box [0.5, 0.5, 1, 1] instead, --detect takes the boxes from the model's own person heads (the bare-tensor forward, csrc/kpd_detect.cu)
+-- both new behaviour, off by default.
 """
 import argparse
 import json
@@ -102,7 +103,7 @@ def format_keypoints(keypoints):
     return lines
 
 
-def predict_single_image(model, image_path, transform, device, gt_path=None, output_path=None, full_image_box=False):
+def predict_single_image(model, image_path, transform, device, gt_path=None, output_path=None, full_image_box=False, detect=False):
     from PIL import Image
     image = Image.open(image_path).convert('RGB')
     x = transform(image).unsqueeze(0)
@@ -110,8 +111,12 @@ def predict_single_image(model, image_path, transform, device, gt_path=None, out
     if boxes is None and full_image_box:
         boxes = torch.tensor([[0.5, 0.5, 1.0, 1.0]])
     batch = {'image': x, 'bboxes': boxes.unsqueeze(0) if boxes is not None else None}
+    if boxes is None and detect:
+        batch = {'image': x}                 # no 'bboxes' key: boxes from the person heads
     with torch.no_grad():
         outputs = model(batch)
+    if boxes is None and detect:
+        boxes = outputs['boxes'][0].cpu()
     keypoints = outputs['keypoints'].squeeze().cpu().numpy()
     for line in format_keypoints(keypoints):
         print(line)
@@ -149,6 +154,7 @@ def main(argv=None):
     parser.add_argument('--device', type=str, default='cuda', help='CUDA device (this build has no CPU path)')
     parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'fp32_strict'])
     parser.add_argument('--full-image-box', action='store_true', help='no label file: use the box [0.5,0.5,1,1]')
+    parser.add_argument('--detect', action='store_true', help='no label file: boxes from the person heads (new behaviour)')
     args = parser.parse_args(argv)
 
     logging.basicConfig(level=logging.INFO, format='%(asctime)s - %(levelname)s - %(message)s')
@@ -163,7 +169,7 @@ def main(argv=None):
     n = 0
     for img, gt in iter_inputs(args.input, args.gt):
         out = Path(args.output) / f"{img.stem}_keypoints{img.suffix}"
-        predict_single_image(model, img, transform, device, gt_path=gt, output_path=out, full_image_box=args.full_image_box)
+        predict_single_image(model, img, transform, device, gt_path=gt, output_path=out, full_image_box=args.full_image_box, detect=args.detect)
         logging.info(f"Saved keypoints to {out.with_name(out.stem + '.json')}")
         n += 1
     logging.info(f"Prediction completed successfully! ({n} image(s))")

@@ -355,6 +355,18 @@ def test_extract_roi_features_matches_torchvision_golden(model):
             np.testing.assert_allclose(got, g["out"][i], rtol=1e-4, atol=1e-4)
 
 
+def test_extract_roi_features_large_map_samplewise_kernel(model):
+    """Maps beyond 392 pixels a side (adaptive grid > 7 samples per bin) take the sample-by-sample ROI-align kernel."""
+    rng = np.random.default_rng(3)
+    feat = torch.from_numpy(rng.standard_normal((1, 4, 460, 460)).astype(np.float32))
+    for box in ([0.5, 0.5, 1.0, 1.0], [0.4, 0.55, 0.7, 0.5]):
+        b = torch.tensor(box, dtype=torch.float32)
+        corners = torch.stack([b[0] - b[2] / 2, b[1] - b[3] / 2, b[0] + b[2] / 2, b[1] + b[3] / 2]).clamp(0, 1) * 460
+        want = OM.roi_align_legacy(feat[0], corners.view(1, 4).numpy())[0].numpy()
+        got = model.extract_roi_features(feat, b)[0].cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=5e-5)
+
+
 def test_person_heads(model, sd):
     g = _golden("person_heads.npz")
     box, cls = model.person_detector.heads(torch.from_numpy(g["x"]), level=0)
