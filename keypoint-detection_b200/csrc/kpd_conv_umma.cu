@@ -99,7 +99,14 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
 // the epilogue of a tile is a dependent chain of tcgen05.ld -> bias/ReLU -> convert -> stores per 32-channel chunk, and with
 // K as short as 576 (head conv 64->256) one warp per lane group cannot drain a tile in the time the MMAs need for the next).
 // TS = TMA-store epilogue (plain convs: no fused pooling / residual / final 1x1, NHWC output).
-template <bool BF16, int MT, int RB, int EW, bool TS>
+// CG = 2: CTA PAIRS (tcgen05 cta_group::2).  The two CTAs of a cluster work on two M-tiles at once; each loads its own A tile and
+// HALF of the weight tile (Cout/2 rows), one thread of the leader CTA issues M = 256 MMAs that read both CTAs' shared memory and
+// write both CTAs' tensor memory.  The tensor core fetches its operands from shared memory at ~64 B/clk; at N = 256 that is
+// exactly what one MMA needs per its math time (A 4 KB + B 8 KB per 182 cycles), so any hiccup starves it -- a pair needs
+// 4 + 4 KB per CTA (profiles/r02_conv_row_shift_tap_reuse.txt).  TMA loads of both CTAs complete on the leader's `full` barrier,
+// tcgen05.commit is multicast to both CTAs' `empty` / `tmem_full` barriers, the peer's epilogue warps arrive on the leader's
+// `tmem_empty` through the cluster address window.  (MT = 1 and the TMA-store epilogue only: the 256-wide head convs.)
+template <bool BF16, int MT, int RB, int EW, bool TS, int CG>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const ConvParams p) {
@@ -109,7 +116,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     //  to LDS -- as generic loads they were the top stall of the epilogue warps)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int A_BYTES = 128 * RB;
-    const int B_BYTES = p.Cout * RB;
+    const int B_BYTES = (p.Cout / CG) * RB;            // CG = 2: this CTA's half of the weight rows
     const int STAGE_BYTES = MT * A_BYTES + B_BYTES;
     uint8_t* stage_out = smem + (size_t)p.stages * STAGE_BYTES;                 // [EW][2][TS_WARP_BYTES], 1024-byte aligned
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (TS ? EW * 2 * TS_WARP_BYTES : 0));
@@ -122,6 +129,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;      // 0 = leader of the pair
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (S + s); };
@@ -135,7 +143,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (TS) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO) : "memory");
         for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EW); }
+        for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CG * EW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sbias[i] = p.bias[i];
@@ -146,18 +154,25 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();      // pair: both CTAs' barriers exist before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // work split: a pair walks pair-groups of CG tiles; the CTA takes tile pg * CG + rank (a short last group repeats the last tile)
+    const int wstart = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, wstep = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     const int n_live = p.n_valid ? min(*p.n_valid, p.N) : p.N;
     const int tiles_n_live = (n_live + p.tn - 1) / p.tn;
     const int total_tiles = tiles_n_live * p.tiles_h * p.tiles_w;
-    const int total_groups = (total_tiles + MT - 1) / MT;      // MT consecutive tiles share every weight stage
+    const int total_groups = CG == 2 ? (total_tiles + 1) / 2 : (total_tiles + MT - 1) / MT;      // MT consecutive tiles (or the pair's two) share every weight stage
     constexpr int BK = RB / (BF16 ? 2 : 4);            // elements per K slab (one swizzled row)
     const int cchunks = p.Cin / BK;
     const int kiters = p.taps * cchunks;
@@ -167,36 +182,44 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {                                // ---------------- TMA producer
             int stage = 0; uint32_t phase = 0;
-            for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+            for (int grp = wstart; grp < total_groups; grp += wstep) {
                 int w0[MT], h0[MT], n0[MT];             // tile origins: decoded once per group, not per K step
 #pragma unroll
                 for (int i = 0; i < MT; i++) {
-                    const int tile = min(grp * MT + i, total_tiles - 1);         // a short last group repeats its last tile
+                    const int tile = min(CG == 2 ? grp * 2 + (int)crank : grp * MT + i, total_tiles - 1);         // a short last group repeats its last tile
                     const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
                     w0[i] = iw * p.tw; h0[i] = ih * p.th; n0[i] = in * p.tn;
                 }
                 int tap = 0, cc = 0, dy = -pad, dx = -pad;
                 for (int kk = 0; kk < kiters; kk++) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
-                    mbar_expect_tx(full_bar(stage), (uint32_t)STAGE_BYTES);
                     const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    if constexpr (CG == 2) {
+                        // the leader arms its barrier for both CTAs' bytes; either CTA's loads complete on it
+                        if (crank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)STAGE_BYTES);
+                        const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+                        tma_load_4d_cg2(sa, &tmA, lbar, cc * BK, w0[0] + dx, h0[0] + dy, n0[0]);
+                        tma_load_2d_cg2(sa + A_BYTES, &tmB, lbar, tap * p.Cin + cc * BK, (int)crank * (p.Cout >> 1));
+                    } else {
+                    mbar_expect_tx(full_bar(stage), (uint32_t)STAGE_BYTES);
 #pragma unroll
                     for (int i = 0; i < MT; i++)
                         tma_load_4d(sa + i * A_BYTES, &tmA, full_bar(stage), cc * BK, w0[i] + dx, h0[i] + dy, n0[i]);
                     tma_load_2d(sa + MT * A_BYTES, &tmB, full_bar(stage), tap * p.Cin + cc * BK, 0);
+                    }
                     if (++cc == cchunks) { cc = 0; tap++; if (++dx == ksz - pad) { dx = -pad; dy++; } }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {                                // ---------------- MMA issuer
+        if (lane == 0 && crank == 0) {                  // ---------------- MMA issuer (pairs: the leader CTA only)
             // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) (1 = bf16, 2 = tf32), K-major both,
             // N>>3 at [17,23), M>>4 at [24,29)
             const uint32_t fmt = BF16 ? 1u : 2u;
-            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.Cout >> 3) << 17) | (((uint32_t)(128 * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-            for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+            for (int grp = wstart; grp < total_groups; grp += wstep) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MT * p.Cout);
@@ -209,12 +232,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int i = 0; i < MT; i++) {
                         const uint64_t adesc = make_sdesc_rb(sa + i * A_BYTES, RB);
 #pragma unroll
-                        for (int k4 = 0; k4 < ksteps; k4++) // 32-byte K steps inside the swizzled row
-                            tc_mma<BF16>(d_tmem + (uint32_t)(i * p.Cout), adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
+                        for (int k4 = 0; k4 < ksteps; k4++) { // 32-byte K steps inside the swizzled row
+                            if constexpr (CG == 2) tc_mma_cg2<BF16>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
+                            else tc_mma<BF16>(d_tmem + (uint32_t)(i * p.Cout), adesc + 2 * k4, bdesc + 2 * k4, idesc, (kk | k4) != 0 ? 1u : 0u);
+                        }
                     }
+                    if constexpr (CG == 2) tc_commit_cg2(empty_bar(stage)); else
                     tc_commit(empty_bar(stage));        // frees this smem stage once the MMAs above retire
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
+                if constexpr (CG == 2) tc_commit_cg2(tfull_bar(acc)); else
                 tc_commit(tfull_bar(acc));              // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
@@ -234,11 +261,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* sbuf = stage_out + (size_t)(warp - 2) * 2 * TS_WARP_BYTES;
         uint32_t nstore = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int grp = blockIdx.x; grp < total_groups; grp += gridDim.x) {
+        for (int grp = wstart; grp < total_groups; grp += wstep) {
           mbar_wait_warp(tfull_bar(acc), acc_phase, lane);
           tc_fence_after();
           for (int ti = ti_beg; ti < ti_end; ti++) {
-            const int tile = grp * MT + ti;
+            const int tile = CG == 2 ? grp * 2 + (int)crank : grp * MT + ti;
             if (tile >= total_tiles) break;
             const int iw = tile % p.tiles_w, ih = (tile / p.tiles_w) % p.tiles_h, in = tile / (p.tiles_w * p.tiles_h);
             const int w = iw * p.tw + rw, h = ih * p.th + rh, n = in * p.tn + rn;
@@ -380,16 +407,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) { if (CG == 2 && crank != 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0)); else mbar_arrive(tempty_bar(acc)); }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (TS && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every tensor store has completed
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();      // pair: neither CTA leaves while the other can still reach its memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        if constexpr (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -581,7 +609,12 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
     const bool ts = !fin && !pool_part && !res && row_bytes == 128 && c.cout % (prec_bf16 && out_bf16 ? 64 : 32) == 0 && (out_bf16 != 0) == (prec_bf16 != 0) && 32 % p.tw == 0;
     const bool ew8 = fin && mt == 4;
     const int ew = ew8 ? 8 : 4;
-    const int stage_bytes = mt * 128 * row_bytes + c.cout * row_bytes;
+    // CTA pairs (cta_group::2) for the 256-wide convs with the TMA-store epilogue and a long K loop: each CTA stages half of the
+    // weight tile.  Measured at C2: conv 256->256 (K = 2304) 0.639 -> 0.624 ms; conv 64->256 (K = 576) 0.207 -> 0.221 ms -- with nine
+    // slabs per tile the pair's cross-CTA hand-offs at every tile boundary cost more than the halved weight fill saves, so short-K
+    // convs stay single-CTA.
+    const bool pair = ts && mt == 1 && c.cout == 256 && c.taps * c.cin >= 1024 && plan->sm_count >= 2;
+    const int stage_bytes = mt * 128 * row_bytes + (pair ? c.cout / 2 : c.cout) * row_bytes;
     const int misc = 1024 /*align*/ + (ts ? ew * 2 * TS_WARP_BYTES : 0) + 8 * (2 * 8 + 4) + 16 + 4 * c.cout + 64 + (pool_part ? 4 * (4 * 32 * 33 + 8 * c.cout) : 0) + (fin ? 4 * 65 * FIN_KP + 16 : 0);
     int stages = (227 * 1024 - misc) / stage_bytes; if (stages > 8) stages = 8;
     if (stages < 2) { set_error("conv_dense_umma: not enough shared memory"); return KPD_ERR_UNSUPPORTED; }
@@ -603,7 +636,7 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         const cuuint64_t K = (cuuint64_t)c.taps * c.cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)c.cout};
         cuuint64_t strides[1] = {K * elt};
-        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)c.cout};
+        cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? c.cout / 2 : c.cout)};
         cuuint32_t es[2] = {1, 1};
         const void* wptr = prec_bf16 ? static_cast<const void*>(c.w_bf16) : static_cast<const void*>(c.w_tf32);
         CUresult r = enc(&tmB, prec_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
@@ -625,13 +658,27 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed: %d", (int)r); return KPD_ERR_STATE; }
     }
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
-    const int grid = std::min((total_tiles + mt - 1) / mt, plan->sm_count);
-    static uint64_t attr[16] = {};
+    int grid = std::min((total_tiles + mt - 1) / mt, plan->sm_count);
+    if (pair) grid = std::min(2 * ((total_tiles + 1) / 2), plan->sm_count & ~1);
+    static uint64_t attr[20] = {};
 #define KPD_LAUNCH_UMMA(BF, MTV, RBV, EWV, TSV, SLOT)                                                                     \
     do {                                                                                                                  \
-        KPD_CUDA(ensure_smem_attr(conv_umma_kernel<BF, MTV, RBV, EWV, TSV>, 227 * 1024, attr[SLOT]));                     \
-        conv_umma_kernel<BF, MTV, RBV, EWV, TSV><<<grid, 64 + 32 * EWV, smem, s>>>(tmA, tmB, tmO, p);                     \
+        KPD_CUDA(ensure_smem_attr(conv_umma_kernel<BF, MTV, RBV, EWV, TSV, 1>, 227 * 1024, attr[SLOT]));                  \
+        conv_umma_kernel<BF, MTV, RBV, EWV, TSV, 1><<<grid, 64 + 32 * EWV, smem, s>>>(tmA, tmB, tmO, p);                  \
     } while (0)
+#define KPD_LAUNCH_UMMA_PAIR(BF, SLOT)                                                                                    \
+    do {                                                                                                                  \
+        KPD_CUDA(ensure_smem_attr(conv_umma_kernel<BF, 1, 128, 4, true, 2>, 227 * 1024, attr[SLOT]));                     \
+        cudaLaunchConfig_t cfg{};                                                                                         \
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 + 32 * 4); cfg.dynamicSmemBytes = smem; cfg.stream = s;          \
+        cudaLaunchAttribute at[1];                                                                                        \
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1; \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                                                 \
+        KPD_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<BF, 1, 128, 4, true, 2>, tmA, tmB, tmO, p));                   \
+    } while (0)
+    if (pair) {
+        if (prec_bf16) KPD_LAUNCH_UMMA_PAIR(true, 15); else KPD_LAUNCH_UMMA_PAIR(false, 16);
+    } else
     if (row_bytes == 64) {
         if (prec_bf16 || mt != 1) { set_error("conv_dense_umma: 64-byte K rows are built for tf32, mt=1"); return KPD_ERR_UNSUPPORTED; }
         KPD_LAUNCH_UMMA(false, 1, 64, 4, false, 0);
@@ -646,6 +693,7 @@ int conv_dense_umma(const kpd_plan* plan, const DenseConv& c, int prec_bf16, con
         if (mt == 4) KPD_LAUNCH_UMMA(false, 4, 128, 4, false, 12); else if (mt == 2) KPD_LAUNCH_UMMA(false, 2, 128, 4, false, 13); else KPD_LAUNCH_UMMA(false, 1, 128, 4, false, 14);
     }
 #undef KPD_LAUNCH_UMMA
+#undef KPD_LAUNCH_UMMA_PAIR
     KPD_LAUNCH_CHECK();
     return 0;
 }
