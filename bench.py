@@ -286,14 +286,21 @@ def measure_tf32_peak():
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-def tf32_denominator(pk, tf32_peak):
-    """kind::tf32 runs at half the kind::f16 rate on the same datapath.  cuBLAS' tf32 GEMM (measured here) stays below that
-    (665-735 TFLOP/s against 839 = bf16 burst / 2), and a hand-written tcgen05 kernel can beat it, so the denominator is the larger
-    of the two: a fraction above 1 would only say that the library kernel is not the hardware's limit."""
+TF32_NOMINAL = 1125.0            # dense tf32 TFLOP/s of a B200 (half of the 2.25 PFLOP/s bf16 figure)
+
+
+def tf32_denominator(pk, tf32_peak, achieved=None):
+    """kind::tf32 runs at half the kind::f16 rate on the same datapath.  No tf32 peak is in MEASURED_PEAKS.json; the two measured
+    proxies are cuBLAS' tf32 GEMM (timed in this run, 665-735 TFLOP/s) and half of the measured bf16 burst (839).  The
+    hand-written CTA-pair conv exceeds both, so when a kernel does, its fraction is quoted against the nominal dense peak instead
+    (a fraction above 1 would only say that the library kernels are not the hardware's limit)."""
     half = pk["burst"] / 2
-    if tf32_peak and tf32_peak > half:
-        return tf32_peak, "cuBLAS tf32 8192^3 burst measured in this run"
-    return half, f"{pk['source']} bf16 burst / 2 (kind::tf32 = half the kind::f16 rate; cuBLAS tf32 measured in this run: {tf32_peak and round(tf32_peak, 1)} TFLOP/s)"
+    proxy, src = (tf32_peak, "cuBLAS tf32 8192^3 burst measured in this run") if (tf32_peak and tf32_peak > half) else \
+        (half, f"{pk['source']} bf16 burst / 2 (cuBLAS tf32 measured in this run: {tf32_peak and round(tf32_peak, 1)} TFLOP/s)")
+    if achieved is not None and achieved > proxy:
+        return TF32_NOMINAL, (f"nominal dense tf32 peak {TF32_NOMINAL:.0f} TFLOP/s -- the kernel exceeds both measured proxies "
+                              f"(cuBLAS tf32 {tf32_peak and round(tf32_peak, 1)}, bf16 burst / 2 = {half:.1f})")
+    return proxy, src
 
 
 def conv2_roofline(kern, n_roi, precision, pk, tf32_peak, traffic):
@@ -304,7 +311,7 @@ def conv2_roofline(kern, n_roi, precision, pk, tf32_peak, traffic):
     if precision == "bf16":
         peak, src = pk["burst"], f"{pk['source']} bf16 burst (MEASURED_PEAKS.json bf16_tflops): the kernel is event-timed alone in a 5-step profiling pass"
     else:
-        peak, src = tf32_denominator(pk, tf32_peak)
+        peak, src = tf32_denominator(pk, tf32_peak, ach)
     return {"bound": "tensor", "kernel": "conv_umma_kernel (head conv 256->256, 3x3)", "achieved": ach, "peak": peak,
             "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": src,
             "flops_per_launch": flops, "ms_per_launch": kern["head_conv2"]}
