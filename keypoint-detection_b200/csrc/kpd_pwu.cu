@@ -16,6 +16,7 @@
 // residual added on the way).  Persistent CTAs walk
 // (128-row tile, column chunk <= 128) items; 2-3 slab stages; two TMEM accumulator stages.
 #include "kpd_tma.cuh"
+#include <vector>
 #include <stdlib.h>
 
 namespace kpd {
@@ -24,9 +25,11 @@ struct PwUParams {
     const float* bias; float* out; const float* res; const float* se_scale;
     uint32_t M; int K, N, Nc, nchunks, tiles_m, total, stages, stage_bytes;
     int act, hw, res_mode, H, W, up, round_tf32, Np;
+    long long* trace;                 // debugging aid (KPD_PWU_TRACE=1): clock64 stamps of CTA 0 [role][event]
     float* out2; int split, n2;       // optional two-tensor output: columns [0, split) -> out [M][split], [split, split + n2) -> out2 [M][n2]
 };
 
+#define PU_TRACE(role, ev) do { if (p.trace && blockIdx.x == 0 && (ev) < 128) p.trace[(role) * 128 + (ev)] = clock64(); } while (0)
 constexpr int PU_EPI_WARPS = 8, PU_THREADS = 192 + 32 * PU_EPI_WARPS, PU_RS = 36, PU_MAXN = 640;
 constexpr int PU_SC_FLOATS = 4 * 576;                         // SE factors staged per tile: (images a 128-row tile can span) x K floats
 constexpr int PU_A = 16384;                                   // one 128 x 32-float slab
@@ -83,10 +86,12 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         if (lane == 0) {                                // ---------------- TMA producer
             int stage = 0; uint32_t phase = 0;
+            int tr0 = 0;
             for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
                 const int tm = item / p.nchunks, n0 = (item - tm * p.nchunks) * p.Nc;
                 for (int sl = 0; sl < nslabs; sl++) {
                     mbar_wait(free_bar(stage), phase ^ 1);
+                    PU_TRACE(0, tr0++);
                     mbar_expect_tx(full_bar(stage), (uint32_t)PU_A + 2u * b_bytes);
                     const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                     tma_load_2d(sa, &tmA, full_bar(stage), sl * 32, tm * 128);
@@ -99,13 +104,14 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         if (lane == 0) {                                // ---------------- MMA issuer
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nc >> 3) << 17) | ((128u >> 4) << 24);
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0; int tr1 = 0;
             for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Nc);
                 for (int sl = 0; sl < nslabs; sl++) {
                     mbar_wait(split_bar(stage), phase);
+                    PU_TRACE(1, tr1++);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
                     const uint64_t a_hi = make_sdesc_rb(sa, 128), a_lo = make_sdesc_rb(sa + PU_A, 128);
@@ -125,7 +131,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp < 6) {                              // ---------------- split warps 2..5: raw fp32 slab -> tf32 hi / lo slabs
         const int t = (warp - 2) * 32 + lane;           // 0..127; float4 f = t + 128 i lives in row f >> 3 at chunk position f & 7
-        int stage = 0; uint32_t phase = 0;
+        int stage = 0; uint32_t phase = 0; int tr2 = 0;
         for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
             const int tm = item / p.nchunks;
             const uint32_t m0 = (uint32_t)tm * 128u;
@@ -145,6 +151,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int sl = 0; sl < nslabs; sl++) {
                 mbar_wait(full_bar(stage), phase);
+                if (t == 0) PU_TRACE(2, tr2++);
                 uint8_t* sp = smem + (size_t)stage * p.stage_bytes;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -167,6 +174,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) mbar_arrive(split_bar(stage));
+                if (t == 0) PU_TRACE(2, tr2++);
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
@@ -175,7 +183,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int cpar = (warp - 6) >> 2;               // chunk parity this warp drains
         const int rr4 = lane >> 3, q = lane & 7;
         float* rt = red + (warp - 6) * (32 * PU_RS);
-        int acc = 0; uint32_t acc_phase = 0;
+        int acc = 0; uint32_t acc_phase = 0; int tr3 = 0;
         for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
             const int tm = item / p.nchunks, n0 = (item - tm * p.nchunks) * p.Nc;
             const uint32_t m0 = (uint32_t)tm * 128u;
@@ -191,7 +199,9 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     roff[it] = ((size_t)(b * (p.H / p.up) + yy / p.up) * (p.W / p.up) + xx / p.up) * p.N;
                 }
             }
+            if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
             mbar_wait_warp(tfull_bar(acc), acc_phase, lane);
+            if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.Nc);
             auto drain = [&](auto actfn) {
@@ -199,6 +209,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r[32];
                     tc_ld32(taddr + c0, r);
                     tc_wait_ld();
+                    if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
                     const float* bp = sbias + n0 + c0;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -209,6 +220,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         *reinterpret_cast<float4*>(rt + lane * PU_RS + 4 * j) = pu_act4(v, actfn);
                     }
                     __syncwarp();
+                    if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
                     // transposed read: lane = (row rr4 of 4, 4 channels q): one warp store covers four 128-byte row segments
                     const int n = n0 + c0 + 4 * q;
                     if (n < p.N && c0 + 4 * q < p.Nc) {                      // columns past the chunk belong to another item
@@ -243,6 +255,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -314,8 +327,28 @@ int pointwise_umma(const PwMma& a, int sm_count, cudaStream_t s) {
     static uint64_t attr = 0;
     KPD_CUDA(ensure_smem_attr(pw_umma_kernel, 227 * 1024, attr));
     const int grid = (int)std::min<int64_t>(total, (int64_t)sm_count);
+    static const bool trace_on = getenv("KPD_PWU_TRACE") != nullptr;
+    static long long* trace_buf = nullptr;
+    if (trace_on) {
+        if (!trace_buf) cudaMalloc(&trace_buf, 4 * 128 * sizeof(long long));
+        cudaMemsetAsync(trace_buf, 0, 4 * 128 * sizeof(long long), s);
+        p.trace = trace_buf;
+    }
     pw_umma_kernel<<<grid, PU_THREADS, smem, s>>>(tmA, tmB, p);
     KPD_LAUNCH_CHECK();
+    if (trace_on) {                                          // debugging only: synchronous dump of CTA 0's timeline (SM clocks)
+        std::vector<long long> h(4 * 128);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long t0 = 0; for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+        const char* roles[4] = {"producer(free ok)", "mma(split ok)", "split(full ok, done)", "epilogue(start, tfull ok, done)"};
+        fprintf(stderr, "kpd pwu trace: M=%u K=%d N=%d Nc=%d items=%d stages=%d grid=%d\n", p.M, p.K, p.N, p.Nc, p.total, p.stages, grid);
+        for (int r = 0; r < 4; r++) {
+            fprintf(stderr, "  %s:", roles[r]);
+            for (int e = 0; e < 60; e++) if (h[r * 128 + e]) fprintf(stderr, " %lld", h[r * 128 + e] - t0);
+            fprintf(stderr, "\n");
+        }
+    }
     return 0;
 }
 
