@@ -177,6 +177,25 @@ int  kpd_detect_persons(const float* d_box, const float* d_cls, int batch, int h
                         float* d_boxes_out, int32_t* d_count, void* d_scratch, void* stream);
 size_t kpd_detect_scratch_bytes(int batch, int top_m);
 
+/* ---- image preparation -------------------------------------------------------------- */
+/* The reference's `ITransform` (dll/data/transforms.py:9-114: OpenCV + Pillow + torchvision on the host, one image at a time)
+ * for a batch of equally sized uint8 images on the device, bit-exact with those libraries (OpenCV 4.13, Pillow 12.2).
+ * d_src [batch,height,width,channels] uint8, channels 1 (gray), 3 (RGB) or 4 (RGBA, alpha ignored).
+ * grayscale != 0 (transforms.py:43-78): RGB2GRAY -> CLAHE(clip_limit, tiles) -> {GaussianBlur 5x5 s1.5 -> medianBlur 5 ->
+ *   Canny(100,200) -> dilate,erode,dilate,erode 3x3 -> GaussianBlur 3x3 -> rescale to the maximum} -> addWeighted(0.7, 0.3)
+ *   -> Image.resize(out_size, BILINEAR) -> /255 -> (x-0.5)/0.5; d_out float32 [batch,1,out_size,out_size].
+ * grayscale == 0 (transforms.py:80-109): per-channel CLAHE -> GaussianBlur 3x3 s0.5 -> resize -> ImageNet mean/std;
+ *   d_out float32 [batch,3,out_size,out_size].
+ * d_scratch: kpd_itransform_scratch_bytes(...) bytes, 256-byte aligned; no allocation and no host synchronisation inside.
+ * kpd_itransform_stage_offsets: byte offsets of the stage planes inside the scratch buffer (tests / visualisation):
+ *   [0] gray or colour planes u8 [B,planes,H,W], [1] CLAHE LUTs u8 [B,planes,tiles,256], [2] CLAHE (rgb: blurred) planes,
+ *   [3] Canny map after hysteresis u8 (2 = edge), [4] blurred edge plane before the rescale, [5] horizontal-pass rows [B,planes,H,S]. */
+size_t kpd_itransform_scratch_bytes(int batch, int height, int width, int grayscale, int tiles_x, int tiles_y, int out_size);
+int  kpd_itransform_stage_offsets(int batch, int height, int width, int grayscale, int tiles_x, int tiles_y, int out_size,
+                                  size_t* offsets /*[6]*/);
+int  kpd_itransform(const uint8_t* d_src, int batch, int height, int width, int channels, int grayscale, double clip_limit,
+                    int tiles_x, int tiles_y, int out_size, float* d_out, void* d_scratch, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* kpd_last_error(void);
 int  kpd_abi_version(void);

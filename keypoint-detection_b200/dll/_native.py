@@ -61,6 +61,9 @@ _SIGNATURES = {
     "kpd_detect_persons": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_float,
                                      C.c_int, C.c_int, _P, _P, _P, _P]),
     "kpd_detect_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "kpd_itransform_scratch_bytes": (C.c_size_t, [C.c_int] * 7),
+    "kpd_itransform_stage_offsets": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_size_t)]),
+    "kpd_itransform": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "kpd_last_error": (C.c_char_p, []),
     "kpd_abi_version": (C.c_int, []),
     "kpd_launch_count": (C.c_int64, [C.c_int]),

@@ -1,7 +1,11 @@
 """ITransform: the image preparation `scripts/predict.py` applies before the model (reference: dll/data/transforms.py:9-114).
 
-Caller-side host glue, NOT part of the GPU hot path (SURVEY.md 8f N2 lists a GPU version as later work): it runs once per
-image on the CPU with OpenCV, exactly like the reference, and produces the [C,S,S] float tensor the model consumes.
+Two executions of the same pipeline:
+  * `ITransform(...)` -- the reference's own host path (OpenCV + Pillow, one image at a time), kept for callers without a GPU
+    tensor at hand;
+  * `ITransform(..., device="cuda")` -- SURVEY.md 8f N2: the whole pipeline as batched CUDA kernels (`kpd_itransform`,
+    csrc/kpd_itransform.cu), bit-exact with the libraries for every byte stage, output already on the device in the
+    [B,C,S,S] float layout the model consumes.  `transform.batch(u8_tensor)` takes [B,H,W,C] uint8 (host or device).
 
   grayscale (default): gray -> CLAHE -> {Gaussian 5x5 sigma 1.5 -> median 5 -> Canny(100,200) -> close/open-like
                        dilate,erode,dilate,erode with a 3x3 box -> Gaussian 3x3 -> rescale to 0..255} -> 0.7*CLAHE + 0.3*edges
@@ -25,8 +29,61 @@ def _cv2():
 
 
 class ITransform:
-    def __init__(self, img_size=224, clip_limit=1.5, tile_size=(8, 8), grayscale=True):
+    def __init__(self, img_size=224, clip_limit=1.5, tile_size=(8, 8), grayscale=True, device=None):
         self.img_size, self.clip_limit, self.tile_size, self.grayscale = img_size, clip_limit, tuple(tile_size), grayscale
+        self.device = None if device is None else torch.device(device)
+        if self.device is not None and self.device.type != "cuda":
+            raise ValueError(f"ITransform(device=...) selects the CUDA pipeline; got {self.device} (omit it for the host path)")
+        self._scratch = {}
+
+    # ---- CUDA pipeline (kpd_itransform)
+    def batch(self, images, return_stages=False):
+        """[B,H,W] / [B,H,W,C] uint8 tensor or array (C = 1, 3 or 4; host or device) -> float32 [B,C',S,S] on the device.
+        With return_stages=True also a dict of the intermediate uint8 planes (gray, clahe, edges, soft, hpass)."""
+        import ctypes as C
+        from .. import _native
+        if self.device is None:
+            raise RuntimeError("ITransform.batch needs ITransform(..., device='cuda')")
+        dev = _native.require_cuda(self.device)
+        x = torch.as_tensor(images)
+        if x.dtype != torch.uint8:
+            raise TypeError(f"ITransform.batch expects uint8 images, got {x.dtype}")
+        if x.dim() == 3:
+            x = x.unsqueeze(-1)
+        if x.dim() != 4 or x.shape[-1] not in (1, 3, 4):
+            raise ValueError(f"ITransform.batch expects [B,H,W] or [B,H,W,C] with C in 1, 3, 4; got {tuple(x.shape)}")
+        x = x.to(dev, non_blocking=True).contiguous()
+        B, H, W, Cn = x.shape
+        S, gray = int(self.img_size), 1 if self.grayscale else 0
+        tx, ty = int(self.tile_size[0]), int(self.tile_size[1])
+        lib = _native.load()
+        geom = (B, H, W, gray, tx, ty, S)
+        with torch.cuda.device(dev):
+            need = lib.kpd_itransform_scratch_bytes(*geom)
+            if need == 0:
+                raise ValueError(f"ITransform.batch: bad geometry {geom}")
+            ws = self._scratch.get(dev)
+            if ws is None or ws.numel() < need:
+                ws = self._scratch[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty((B, 1 if gray else 3, S, S), dtype=torch.float32, device=dev)
+            _native.check(lib.kpd_itransform(_native.ptr(x), B, H, W, Cn, gray, float(self.clip_limit), tx, ty, S,
+                                             _native.ptr(out), _native.ptr(ws), _native.stream_ptr(dev)), "kpd_itransform")
+            if not return_stages:
+                return out
+            off = (C.c_size_t * 6)()
+            _native.check(lib.kpd_itransform_stage_offsets(*geom, off), "kpd_itransform_stage_offsets")
+            P = 1 if gray else 3
+            def plane(i, shape):
+                n = 1
+                for d in shape:
+                    n *= d
+                return ws[off[i]:off[i] + n].view(shape).clone()
+            stages = {"plane": plane(0, (B, P, H, W)), "lut": plane(1, (B, P, ty, tx, 256)), "clahe": plane(2, (B, P, H, W)),
+                      "hpass": plane(5, (B, P, H, S))}
+            if gray:
+                stages["edges"] = (plane(3, (B, P, H, W)) == 2).to(torch.uint8) * 255
+                stages["soft"] = plane(4, (B, P, H, W))
+            return out, stages
 
     # ---- stage functions (same names as the reference's methods: callers use them directly for visualisation)
     def to_grayscale_clahe(self, img):
@@ -59,6 +116,9 @@ class ITransform:
 
     def __call__(self, img):
         """PIL image (or HxW / HxWx3 uint8 array) -> float32 tensor [1,S,S] (grayscale) or [3,S,S] (rgb)."""
+        if self.device is not None:
+            a = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.array(img))
+            return self.batch(a.unsqueeze(0))[0]
         if not isinstance(img, Image.Image):
             img = Image.fromarray(np.asarray(img))
         staged = self.to_grayscale_clahe(img) if self.grayscale else self.to_rgb_clahe(img)

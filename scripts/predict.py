@@ -155,6 +155,8 @@ def main(argv=None):
     parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32', 'fp32_strict'])
     parser.add_argument('--full-image-box', action='store_true', help='no label file: use the box [0.5,0.5,1,1]')
     parser.add_argument('--detect', action='store_true', help='no label file: boxes from the person heads (new behaviour)')
+    parser.add_argument('--host-transform', action='store_true', help="run ITransform with OpenCV on the host like the reference "
+                        "(default: the bit-identical CUDA pipeline, kpd_itransform)")
     args = parser.parse_args(argv)
 
     logging.basicConfig(level=logging.INFO, format='%(asctime)s - %(levelname)s - %(message)s')
@@ -163,7 +165,8 @@ def main(argv=None):
     from dll.data.transforms import ITransform
     backbone = config['model']['backbone']
     transform = ITransform(img_size=backbone['input_size'], clip_limit=2.0, tile_size=(8, 8),
-                           grayscale=backbone.get('in_channels', 3) == 1 or backbone.get('convert_to_grayscale', False))
+                           grayscale=backbone.get('in_channels', 3) == 1 or backbone.get('convert_to_grayscale', False),
+                           device=None if args.host_transform else device)
     logging.info(f"Loading model from {args.model}")
     model = load_model(args.model, config, device, args.precision)
     n = 0
