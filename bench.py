@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: 256 at N=1, 4096/N at N>1)")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--persons", type=int, default=1)
-    ap.add_argument("--sub", default=None, help="comma list of sub-records at N=1: fp32,c4,c5 (default all; '' = none)")
+    ap.add_argument("--sub", default=None, help="comma list of sub-records at N=1: fp32,c4,c5,itransform (default all; '' = none)")
+    ap.add_argument("--it-batch", type=int, default=256)
     ap.add_argument("--c4-instances", type=int, default=65536)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -416,6 +417,66 @@ def sub_c4(args, pk):
     return out
 
 
+def sub_itransform(lib, args, pk, steps):
+    """the reference's `ITransform` (OpenCV + Pillow on the host) as `kpd_itransform` -- B RGB uint8 images of
+    480x640 -> float [B,1,224,224].  Resident = uint8 batch already in HBM; e2e = pinned uint8 batch copied inside the timed
+    region (PCIe-bound: 0.92 MB per image); the host libraries timed beside it on a bounded sample, all host threads."""
+    import ctypes as C
+    from dll.data import ITransform
+    B, H, W, S = args.it_batch, 480, 640, 224
+
+    def synth_photo(seed):                      # photo-like: smooth illumination, hard-edged shapes, sensor noise
+        rng = np.random.default_rng(seed)
+        yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+        img = np.stack([120 + 70 * np.sin(xx / (19.0 + 3 * c) + seed) * np.cos(yy / (27.0 - 2 * c)) + 25 * np.sin((xx + 2 * yy) / (7.0 + c))
+                        for c in range(3)], axis=-1)
+        for k in range(6):
+            cy, cx, ry, rx = rng.uniform(0, H), rng.uniform(0, W), rng.uniform(H / 12, H / 4), rng.uniform(W / 12, W / 4)
+            m = ((np.abs(yy - cy) < ry) & (np.abs(xx - cx) < rx)) if k % 2 else (((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1)
+            img[m] += rng.uniform(-80, 80, 3)
+        return np.clip(img + rng.normal(0, 5, img.shape), 0, 255).astype(np.uint8)
+
+    uniq = [synth_photo(500 + i) for i in range(8)]
+    host = torch.from_numpy(np.stack([uniq[i % 8] for i in range(B)])).pin_memory()
+    dev_u8 = host.cuda()
+    t = ITransform(S, 2.0, (8, 8), True, device="cuda")
+    out = t.batch(dev_u8)
+    torch.cuda.synchronize()
+    host_t = ITransform(S, 2.0, (8, 8), True)                                   # the reference's own host pipeline (cv2 + Pillow)
+    exact = bool(np.array_equal(out[3].cpu().numpy(), host_t(uniq[3]).numpy()))
+    sampler = ClockSampler(torch.cuda.current_device()).start()
+    lib.kpd_launch_count(1)
+    ms = ev_time(lambda: t.batch(dev_u8), steps)
+    launches = lib.kpd_launch_count(0) // (steps + 3)
+    ms_e2e = ev_time(lambda: t.batch(host.cuda(non_blocking=True))[0, 0, 0, :8].cpu(), steps)
+    clocks = sampler.stop()
+    lib.kpd_profile_enable(2)
+    for _ in range(3):
+        t.batch(dev_u8)
+    torch.cuda.synchronize()
+    kern = {}
+    for tag in ("itransform", "itransform.lut", "itransform.clahe_canny", "itransform.hysteresis", "itransform.morph", "itransform.hresize", "itransform.vresize"):
+        tt, n = C.c_double(0), C.c_int64(0)
+        if lib.kpd_profile_read(tag.encode(), C.byref(tt), C.byref(n)) == 0 and n.value:
+            kern[tag] = tt.value / n.value
+    lib.kpd_profile_enable(0)
+    n_cpu, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < 4.0:
+        host_t(uniq[n_cpu % 8]); n_cpu += 1
+    cpu_ips = n_cpu / (time.perf_counter() - t0)
+    algo = B * (H * W * 3 + S * S * 4)
+    return {"workload": f"N2 ITransform grayscale pipeline: {B} x 480x640x3 uint8 -> [{B},1,224,224] float32 (clip 2.0, 8x8 tiles)",
+            "value": B / ms * 1e3, "unit": "images/sec", "ms_per_batch": ms, "gpu_launches": int(launches),
+            "e2e": {"value": B / ms_e2e * 1e3, "unit": "images/sec", "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": 32,
+                    "note": "serial copy + kernels on one stream; 0.92 MB of uint8 per image over PCIe"},
+            "bit_exact_vs_host_libraries": exact, "kernels_ms": kern, "algorithmic_bytes": algo,
+            "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": algo / ms / 1e6 / pk["hbm"],
+                         "note": "whole pipeline against its layer-boundary bytes (RGB in, float out); the stencil stages are issue-bound byte work"},
+            "cpu_baseline": {"value": cpu_ips, "unit": "images/sec", "cores": os.cpu_count(), "kind": "reference",
+                             "sample": f"{n_cpu} images through the reference's own pipeline (cv2 {__import__('cv2').__version__} + Pillow), one image at a time"},
+            "clocks": clocks}
+
+
 def sub_c5(model, lib, args, pk, dev, steps):
     """BASELINE config C5: B=128 images of 512x512 with P=3 seeded boxes through the model, the person heads (1x1 box/cls
     convs, person_head.py:27-34) on the resulting FPN-0 map, and NMS (person_head.py:96-139) over 128 x 100 seeded candidates."""
@@ -589,7 +650,7 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
-    subs_wanted = (args.sub if args.sub is not None else ("fp32,c4,c5" if world == 1 else "")).split(",")
+    subs_wanted = (args.sub if args.sub is not None else ("fp32,c4,c5,itransform" if world == 1 else "")).split(",")
     subs_wanted = [s for s in subs_wanted if s]
     tf32_peak = measure_tf32_peak() if (world == 1) else None
     ms_step = ms / args.steps
@@ -636,6 +697,8 @@ def main():
         sub["fp32"] = sub_fp32(model, lib, args, pk, tf32_peak, dev, steps_sub)
     if "c5" in subs_wanted:
         sub["c5"] = sub_c5(model, lib, args, pk, dev, steps_sub)
+    if "itransform" in subs_wanted:
+        sub["itransform"] = sub_itransform(lib, args, pk, steps_sub)
     if "c4" in subs_wanted:
         model._workspace = type(model._workspace)()      # drop the C5 workspace before the 20 GB of heat maps are allocated
         torch.cuda.empty_cache()

@@ -7,10 +7,11 @@
 //
 // All stages are HBM / L2-bound integer work on 1-byte pixels, so the design is about touching every plane once:
 //   clahe_lut_kernel      one CTA per (plane, CLAHE tile): gray conversion + shared-memory histogram + clip / redistribute / scan -> LUT
-//   clahe_canny_kernel    one CTA per 32x64 tile (+6 halo): CLAHE blend -> Gaussian -> median -> Sobel -> NMS, stage to stage in
+//   clahe_canny_kernel    one CTA per 64x64 tile (+6 halo): CLAHE blend -> Gaussian -> median -> Sobel -> NMS, stage to stage in
 //                         shared memory; writes the CLAHE plane and the Canny map (0 candidate / 1 none / 2 strong)
-//   hysteresis_kernel     persistent cooperative grid: tile-local flood fill in shared memory, rounds separated by a grid barrier
-//   morph_kernel          edges -> dilate -> erode -> dilate -> erode -> Gaussian 3x3 in one tile pass (+5 halo) + per-image maximum
+//   hysteresis_kernel     persistent cooperative grid; a warp holds a tile as 64-bit row masks (lane = row) and floods it with
+//                         shifts and lane shuffles; dirty-tile rounds separated by a grid barrier
+//   morph_kernel          edges -> dilate -> erode -> dilate -> erode on the same row masks -> Gaussian 3x3 + per-image maximum
 //   blend_hresize_kernel  rescale LUT + addWeighted on the fly + horizontal pass of Pillow's fixed-point triangle filter
 //   vresize_norm_kernel   vertical pass + ToTensor + Normalize -> float [B,C,S,S]
 // Border rules differ per stage (reflect-101, replicate, ignore, zero); every shared-memory stage array therefore holds, at
@@ -23,9 +24,8 @@ namespace kpd {
 namespace {
 
 constexpr int IT_THREADS = 256;
-constexpr int TH = 32, TW = 64;                 // output tile of the fused stencil kernels
+constexpr int TH = 32, TW = 64;                 // output tile of the rgb stencil kernel
 constexpr int HALO_C = 6;                       // gauss 2 + median 2 + sobel 1 + nms 1
-constexpr int HALO_M = 5;                       // 4 morphology steps + gauss 1
 
 struct ITParams {
     const uint8_t* src; int B, H, W, C;         // source [B][H][W][C] uint8, C in {1,3,4}
@@ -63,15 +63,15 @@ clahe_lut_kernel(ITParams p, uint8_t* __restrict__ plane, uint8_t* __restrict__ 
     const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
     for (int i = t; i < 8 * 256; i += IT_THREADS) (&hist[0][0])[i] = 0;
     __syncthreads();
-    const int area = p.tw * p.th;
     uint8_t* dst = plane + (size_t)pl * p.H * p.W;
-    for (int i = t; i < area; i += IT_THREADS) {
-        const int yy = i / p.tw, xx = i - yy * p.tw;
-        const int ye = ty * p.th + yy, xe = tx * p.tw + xx;            // coordinates in the padded image
-        const int y = reflect101(ye, p.H), x = reflect101(xe, p.W);    // copyMakeBorder(BORDER_REFLECT_101) on the bottom / right
-        const uint32_t v = plane_px(p, b, c, y, x);
-        if (ye < p.H && xe < p.W) dst[(size_t)y * p.W + x] = (uint8_t)v;
-        atomicAdd(&hist[warp][v], 1u);
+    for (int yy = warp; yy < p.th; yy += IT_THREADS / 32) {            // a warp per tile row, lanes along x
+        const int ye = ty * p.th + yy, y = reflect101(ye, p.H);       // copyMakeBorder(BORDER_REFLECT_101) on the bottom / right
+        for (int xx = lane; xx < p.tw; xx += 32) {
+            const int xe = tx * p.tw + xx, x = reflect101(xe, p.W);
+            const uint32_t v = plane_px(p, b, c, y, x);
+            if (ye < p.H && xe < p.W) dst[(size_t)y * p.W + x] = (uint8_t)v;
+            atomicAdd(&hist[warp][v], 1u);
+        }
     }
     __syncthreads();
     uint32_t h = 0;
@@ -128,7 +128,8 @@ __device__ __forceinline__ uint8_t clahe_px(const ClaheGeom& g, const uint8_t* _
 
 // ------------------------------------------------------------------------------------------------ median of 25
 // Forgetful selection: of 14 values neither the minimum nor the maximum can be the 13th of 25; drop both, take the next value in.
-#define IT_CE(a, b) { const uint32_t _lo = min(a, b); b = max(a, b); a = _lo; }
+// values are two pixels packed as u16x2: VIMNMX.U16x2 orders both at once
+#define IT_CE(a, b) { const uint32_t _lo = __vminu2(a, b); b = __vmaxu2(a, b); a = _lo; }
 template <int N> __device__ __forceinline__ void ends_minmax(uint32_t (&v)[14]) {      // min -> v[0], max -> v[N-1]
 #pragma unroll
     for (int i = 0; i < N / 2; i++) IT_CE(v[i], v[N - 1 - i]);
@@ -152,55 +153,83 @@ template <> struct Forget<3> {
 };
 
 // ------------------------------------------------------------------------------------------------ CLAHE -> ... -> Canny map
-constexpr int RC_H = TH + 2 * HALO_C, RC_W = TW + 2 * HALO_C;        // 44 x 76 region
+constexpr int CT_H = 64, CT_W = 64;                                   // output tile; region = tile + 6 halo on each side
+constexpr int RC_H = CT_H + 2 * HALO_C, RC_W = CT_W + 2 * HALO_C;    // 76 x 76
+struct ClaheAxis { int pos, off1, off2; float a, a1; };               // per region column / row: source coordinate, LUT offsets of the two tiles, weights
 __global__ void __launch_bounds__(IT_THREADS)
 clahe_canny_kernel(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ lut, ClaheGeom g, int H, int W, int low, int high,
                    uint8_t* __restrict__ clahe, uint8_t* __restrict__ pmap) {
     __shared__ uint8_t s_c[RC_H * RC_W];         // CLAHE, extended by reflect-101 (GaussianBlur's border)
     __shared__ uint8_t s_g[RC_H * RC_W];         // Gaussian, extended by replication (medianBlur's border)
     __shared__ uint8_t s_m[RC_H * RC_W];         // median, extended by replication (Canny's Sobel border)
-    __shared__ uint16_t s_mag[RC_H * RC_W];      // |dx| + |dy|, zero outside the image
+    __shared__ uint16_t s_mag[RC_H * RC_W];      // horizontal Gaussian pass (Q8), later |dx| + |dy| (zero outside the image)
+    __shared__ ClaheAxis s_ax[RC_W], s_ay[RC_H];
     const int t = threadIdx.x, b = blockIdx.z;
-    const int x0 = blockIdx.x * TW - HALO_C, y0 = blockIdx.y * TH - HALO_C;
+    const int x0 = blockIdx.x * CT_W - HALO_C, y0 = blockIdx.y * CT_H - HALO_C;
     const uint8_t* gp = gray + (size_t)b * H * W;
     const uint8_t* lp = lut + (size_t)b * g.tiles_x * g.tiles_y * 256;
+    // CLAHE blend geometry is separable: one entry per region column and row (clahe.cpp computes the same tables per image)
+    if (t < RC_W + RC_H) {
+        const bool col = t < RC_W;
+        const int i = col ? t : t - RC_W;
+        const int n = col ? W : H, nt = col ? g.tiles_x : g.tiles_y;
+        const int pos = clampi(reflect101((col ? x0 : y0) + i, n), n);          // far outside (never consumed): keep the address valid
+        const float tf = __fsub_rn(__fmul_rn((float)pos, col ? g.inv_tw : g.inv_th), 0.5f);
+        int t1 = (int)floorf(tf);
+        const float a = __fsub_rn(tf, (float)t1);
+        const int t2 = min(t1 + 1, nt - 1); t1 = max(t1, 0);
+        const int stride = col ? 256 : g.tiles_x * 256;
+        ClaheAxis e{pos, t1 * stride, t2 * stride, a, __fsub_rn(1.0f, a)};
+        if (col) s_ax[i] = e; else s_ay[i] = e;
+    }
+    __syncthreads();
     for (int i = t; i < RC_H * RC_W; i += IT_THREADS) {
         const int v = i / RC_W, u = i - v * RC_W;
-        const int y = reflect101(y0 + v, H), x = reflect101(x0 + u, W);
-        const int yc = clampi(y, H), xc = clampi(x, W);                 // far outside (never consumed): keep the address valid
-        s_c[i] = clahe_px(g, lp, xc, yc, gp[(size_t)yc * W + xc]);
+        const ClaheAxis ax = s_ax[u], ay = s_ay[v];
+        const uint8_t* l = lp + gp[(size_t)ay.pos * W + ax.pos];
+        const float l11 = (float)__ldg(l + ay.off1 + ax.off1), l12 = (float)__ldg(l + ay.off1 + ax.off2);
+        const float l21 = (float)__ldg(l + ay.off2 + ax.off1), l22 = (float)__ldg(l + ay.off2 + ax.off2);
+        const float top = __fadd_rn(__fmul_rn(l11, ax.a1), __fmul_rn(l12, ax.a));
+        const float bot = __fadd_rn(__fmul_rn(l21, ax.a1), __fmul_rn(l22, ax.a));
+        s_c[i] = sat_rint(__fadd_rn(__fmul_rn(top, ay.a1), __fmul_rn(bot, ay.a)));
     }
     __syncthreads();
     // interior of the CLAHE plane leaves here
-    for (int i = t; i < TH * TW; i += IT_THREADS) {
-        const int v = i / TW, u = i - v * TW, y = y0 + HALO_C + v, x = x0 + HALO_C + u;
+    for (int i = t; i < CT_H * CT_W; i += IT_THREADS) {
+        const int v = i / CT_W, u = i - v * CT_W, y = y0 + HALO_C + v, x = x0 + HALO_C + u;
         if (y < H && x < W) clahe[((size_t)b * H + y) * W + x] = s_c[(v + HALO_C) * RC_W + u + HALO_C];
     }
-    // Gaussian 5x5 sigma 1.5 in fixed point: taps 31 60 74 60 31 (Q8), one rounding (x + 2^15) >> 16
+    // Gaussian 5x5 sigma 1.5 in fixed point: taps 31 60 74 60 31 (Q8) per axis, one rounding (x + 2^15) >> 16.
+    // Columns / rows outside the image take the value at the clamped coordinate (what the median's replicate border sees).
+    for (int i = t; i < RC_H * (RC_W - 4); i += IT_THREADS) {
+        const int v = i / (RC_W - 4), u = i % (RC_W - 4) + 2;
+        const uint8_t* r = s_c + v * RC_W + clampi(x0 + u, W) - x0;
+        s_mag[v * RC_W + u] = (uint16_t)(31u * (r[-2] + r[2]) + 60u * (r[-1] + r[1]) + 74u * r[0]);
+    }
+    __syncthreads();
     for (int i = t; i < (RC_H - 4) * (RC_W - 4); i += IT_THREADS) {
         const int v = i / (RC_W - 4) + 2, u = i % (RC_W - 4) + 2;
-        const int ym = clampi(y0 + v, H) - y0, xm = clampi(x0 + u, W) - x0;       // value the median's replicate border sees
-        uint32_t acc = 0;
-#pragma unroll
-        for (int dy = -2; dy <= 2; dy++) {
-            const uint8_t* r = s_c + (ym + dy) * RC_W + xm;
-            const uint32_t hrow = 31u * (r[-2] + r[2]) + 60u * (r[-1] + r[1]) + 74u * r[0];
-            acc += hrow * (dy == 0 ? 74u : ((dy == -1 || dy == 1) ? 60u : 31u));
-        }
+        const uint16_t* r = s_mag + (clampi(y0 + v, H) - y0) * RC_W + u;
+        const uint32_t acc = 31u * ((uint32_t)r[-2 * RC_W] + r[2 * RC_W]) + 60u * ((uint32_t)r[-RC_W] + r[RC_W]) + 74u * r[0];
         s_g[v * RC_W + u] = (uint8_t)min((acc + (1u << 15)) >> 16, 255u);
     }
     __syncthreads();
-    // median 5x5
-    for (int i = t; i < (RC_H - 8) * (RC_W - 8); i += IT_THREADS) {
-        const int v = i / (RC_W - 8) + 4, u = i % (RC_W - 8) + 4;
-        const int ym = clampi(y0 + v, H) - y0, xm = clampi(x0 + u, W) - x0;       // value Sobel's replicate border sees
+    // median 5x5, two horizontally adjacent pixels per thread (u16x2 lanes)
+    constexpr int MPAIRS = (RC_W - 8) / 2;
+    for (int i = t; i < (RC_H - 8) * MPAIRS; i += IT_THREADS) {
+        const int v = i / MPAIRS + 4, u = (i % MPAIRS) * 2 + 4;
+        const int ym = clampi(y0 + v, H) - y0;                                    // value Sobel's replicate border sees
+        const int xa = clampi(x0 + u, W) - x0, xb = clampi(x0 + u + 1, W) - x0;
         uint32_t w14[14], rest[11];
 #pragma unroll
         for (int k = 0; k < 25; k++) {
-            const uint32_t px = s_g[(ym + k / 5 - 2) * RC_W + xm + k % 5 - 2];
+            const uint8_t* r = s_g + (ym + k / 5 - 2) * RC_W + k % 5 - 2;
+            const uint32_t px = (uint32_t)r[xa] | ((uint32_t)r[xb] << 16);
             if (k < 14) w14[k] = px; else rest[k - 14] = px;
         }
-        s_m[v * RC_W + u] = (uint8_t)Forget<14>::run(w14, rest);
+        const uint32_t med = Forget<14>::run(w14, rest);
+        s_m[v * RC_W + u] = (uint8_t)(med & 0xffu);
+        s_m[v * RC_W + u + 1] = (uint8_t)(med >> 16);
     }
     __syncthreads();
     // Sobel magnitude |dx| + |dy| on the region shrunk by 5; zero outside the image
@@ -218,8 +247,8 @@ clahe_canny_kernel(const uint8_t* __restrict__ gray, const uint8_t* __restrict__
     }
     __syncthreads();
     // non-maximum suppression with the integer tan(22.5 deg) sector test, thresholds: 2 strong, 0 candidate, 1 none
-    for (int i = t; i < TH * TW; i += IT_THREADS) {
-        const int v = i / TW + HALO_C, u = i % TW + HALO_C;
+    for (int i = t; i < CT_H * CT_W; i += IT_THREADS) {
+        const int v = i / CT_W + HALO_C, u = i % CT_W + HALO_C;
         const int y = y0 + v, x = x0 + u;
         if (y >= H || x >= W) continue;
         const uint16_t* mp = s_mag + v * RC_W + u;
@@ -244,13 +273,42 @@ clahe_canny_kernel(const uint8_t* __restrict__ gray, const uint8_t* __restrict__
     }
 }
 
+// ------------------------------------------------------------------------------------------------ row bit masks
+// Hysteresis and the morphology chain work on binary images: a warp owns a 64 x 32 window as one 64-bit mask per row
+// (lane r = row r), so a 3x3 step over 2048 pixels is a handful of shifts, logic ops and two lane shuffles.
+struct RowMasks { uint64_t strong, cand, valid; };      // map == 2, map == 0, inside the image
+__device__ __forceinline__ RowMasks load_rows(const uint8_t* __restrict__ gp, int H, int W, int x0, int y0, int lane) {
+    RowMasks m{0, 0, 0};
+    const int xa = x0 + lane, xb = xa + 32;
+    const bool ina = xa >= 0 && xa < W, inb = xb >= 0 && xb < W;
+#pragma unroll 4
+    for (int r = 0; r < 32; r++) {
+        const int y = y0 + r;
+        const bool iny = y >= 0 && y < H;
+        uint32_t pa = 1, pb = 1;
+        if (iny && ina) pa = __ldcg(gp + (size_t)y * W + xa);
+        if (iny && inb) pb = __ldcg(gp + (size_t)y * W + xb);
+        const uint32_t s_lo = __ballot_sync(0xffffffffu, pa == 2), s_hi = __ballot_sync(0xffffffffu, pb == 2);
+        const uint32_t c_lo = __ballot_sync(0xffffffffu, pa == 0), c_hi = __ballot_sync(0xffffffffu, pb == 0);
+        const uint32_t v_lo = __ballot_sync(0xffffffffu, iny && ina), v_hi = __ballot_sync(0xffffffffu, iny && inb);
+        if (lane == r) {
+            m.strong = (uint64_t)s_lo | ((uint64_t)s_hi << 32);
+            m.cand = (uint64_t)c_lo | ((uint64_t)c_hi << 32);
+            m.valid = (uint64_t)v_lo | ((uint64_t)v_hi << 32);
+        }
+    }
+    return m;
+}
+__device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int lane) { const uint64_t r = __shfl_up_sync(0xffffffffu, v, 1); return lane == 0 ? 0ull : r; }
+__device__ __forceinline__ uint64_t shfl_dn64(uint64_t v, int lane) { const uint64_t r = __shfl_down_sync(0xffffffffu, v, 1); return lane == 31 ? 0ull : r; }
+
 // ------------------------------------------------------------------------------------------------ hysteresis
-// Persistent grid (cooperative launch: every CTA resident).  A round = every tile floods its strong pixels into its
-// candidates in shared memory until nothing changes; tiles whose pixels changed publish them and raise the round's flag;
-// rounds repeat (grid barrier in between) until a round changes nothing.  The fixed point is unique, so the result
-// does not depend on the sweep order.
+// Persistent grid (cooperative launch: every CTA resident), one warp per 62 x 30 tile (+1 halo).  A round = every dirty tile
+// floods its strong pixels into its candidates until nothing changes; a tile that changed publishes its new edge pixels
+// and marks itself and its 8 neighbours dirty for the next round; rounds (grid barrier in between) repeat until none is
+// dirty.  The fixed point is unique, so the result does not depend on the order.
 struct HystCtl { unsigned int barrier; unsigned int flag[3]; };
-constexpr int HT_H = 32, HT_W = 64, HS_W = HT_W + 2 + 2;             // padded row (68) keeps 4-byte alignment irrelevant: byte accesses only
+constexpr int HY_IW = 62, HY_IH = 30;
 __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -263,129 +321,112 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
     __syncthreads();
 }
 __global__ void __launch_bounds__(IT_THREADS)
-hysteresis_kernel(uint8_t* __restrict__ pmap, int B, int H, int W, int tiles_x, int tiles_y, uint8_t* __restrict__ tile_live, HystCtl* ctl) {
-    __shared__ uint8_t s[(HT_H + 2) * HS_W];
-    const int t = threadIdx.x;
-    const int ntiles = B * tiles_x * tiles_y;
+hysteresis_kernel(uint8_t* __restrict__ pmap, int B, int H, int W, int tiles_x, int tiles_y, uint8_t* __restrict__ dirty, HystCtl* ctl) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * (IT_THREADS / 32) + (threadIdx.x >> 5), nw = gridDim.x * (IT_THREADS / 32);
+    const int per_img = tiles_x * tiles_y, ntiles = B * per_img;
+    const uint64_t interior = (lane >= 1 && lane <= HY_IH) ? 0x7ffffffffffffffeull : 0ull;
     for (unsigned int round = 0;; round++) {
-        int cta_changed = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if (round > 0 && !tile_live[tile]) continue;                       // no candidate left in this tile
-            const int b = tile / (tiles_x * tiles_y), r = tile - b * tiles_x * tiles_y;
-            const int y0 = (r / tiles_x) * HT_H - 1, x0 = (r % tiles_x) * HT_W - 1;
+        uint8_t* d_now = dirty + (size_t)(round & 1) * ntiles;
+        uint8_t* d_next = dirty + (size_t)((round + 1) & 1) * ntiles;
+        bool marked = false;
+        for (int tile = gw; tile < ntiles; tile += nw) {
+            if (round > 0) {
+                if (!__ldcg(d_now + tile)) continue;
+                __syncwarp();
+                if (lane == 0) d_now[tile] = 0;
+            }
+            const int b = tile / per_img, r = tile - b * per_img, ty = r / tiles_x, tx = r - ty * tiles_x;
+            const int y0 = ty * HY_IH - 1, x0 = tx * HY_IW - 1;
             uint8_t* gp = pmap + (size_t)b * H * W;
-            int has_strong = 0, has_cand = 0;
-            for (int i = t; i < (HT_H + 2) * (HT_W + 2); i += IT_THREADS) {
-                const int v = i / (HT_W + 2), u = i - v * (HT_W + 2);
-                const int y = y0 + v, x = x0 + u;
-                uint8_t px = 1;
-                if (y >= 0 && y < H && x >= 0 && x < W) px = gp[(size_t)y * W + x];
-                s[v * HS_W + u] = px;
-                has_strong |= (px == 2);
-                has_cand |= (px == 0 && v >= 1 && v <= HT_H && u >= 1 && u <= HT_W);
+            const RowMasks m = load_rows(gp, H, W, x0, y0, lane);
+            const uint64_t C = m.cand & interior;
+            uint64_t S = m.strong;
+            if (!__any_sync(0xffffffffu, C != 0) || !__any_sync(0xffffffffu, S != 0)) continue;
+            bool grew;
+            do {
+                const uint64_t n = S | (S << 1) | (S >> 1);
+                const uint64_t add = C & ~S & (n | shfl_up64(n, lane) | shfl_dn64(n, lane));
+                S |= add;
+                grew = __any_sync(0xffffffffu, add != 0);
+            } while (grew);
+            const uint64_t fresh = S & ~m.strong;
+            if (!__any_sync(0xffffffffu, fresh != 0)) continue;
+            for (int rr = 1; rr <= HY_IH; rr++) {
+                const uint64_t f = __shfl_sync(0xffffffffu, fresh, rr);
+                if (f == 0) continue;
+                uint8_t* row = gp + (size_t)(y0 + rr) * W + x0;
+                if ((f >> lane) & 1ull) row[lane] = 2;
+                if ((f >> (lane + 32)) & 1ull) row[lane + 32] = 2;
             }
-            has_strong = __syncthreads_or(has_strong);
-            has_cand = __syncthreads_or(has_cand);
-            if (t == 0) tile_live[tile] = (uint8_t)(has_cand != 0);
-            int tile_changed = 0;
-            if (has_strong && has_cand) {
-                int c;
-                do {
-                    c = 0;
-                    for (int i = t; i < HT_H * HT_W; i += IT_THREADS) {
-                        const int v = i / HT_W + 1, u = i % HT_W + 1;
-                        uint8_t* q = s + v * HS_W + u;
-                        if (*q == 0) {
-                            const bool hit = q[-HS_W - 1] == 2 || q[-HS_W] == 2 || q[-HS_W + 1] == 2 || q[-1] == 2 || q[1] == 2 ||
-                                             q[HS_W - 1] == 2 || q[HS_W] == 2 || q[HS_W + 1] == 2;
-                            if (hit) { *q = 2; c = 1; }
-                        }
-                    }
-                    c = __syncthreads_or(c);
-                    tile_changed |= c;
-                } while (c);
+            if (lane < 9) {                                                   // the 8 tiles around this one see new pixels in their halo
+                const int ny = ty + lane / 3 - 1, nx = tx + lane % 3 - 1;
+                if (ny >= 0 && ny < tiles_y && nx >= 0 && nx < tiles_x && lane != 4) d_next[b * per_img + ny * tiles_x + nx] = 1;
             }
-            if (tile_changed) {
-                for (int i = t; i < HT_H * HT_W; i += IT_THREADS) {
-                    const int v = i / HT_W + 1, u = i % HT_W + 1;
-                    const int y = y0 + v, x = x0 + u;
-                    if (y < H && x < W && s[v * HS_W + u] == 2) gp[(size_t)y * W + x] = 2;
-                }
-                cta_changed = 1;
-            }
-            __syncthreads();
+            marked = true;
         }
-        if (cta_changed && t == 0) atomicExch(&ctl->flag[round % 3], 1u);
+        if (marked && lane == 0) atomicExch(&ctl->flag[round % 3], 1u);
         grid_barrier(&ctl->barrier, (round + 1) * gridDim.x);
         unsigned int f;
         asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(f) : "l"(&ctl->flag[round % 3]) : "memory");
-        if (blockIdx.x == 0 && t == 0) ctl->flag[(round + 2) % 3] = 0;        // last read before this round's barrier, next written after the next one
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->flag[(round + 2) % 3] = 0;   // last read before this round's barrier, next written after the next one
         if (!f) break;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ morphology + soft edges
-constexpr int RM_H = TH + 2 * HALO_M, RM_W = TW + 2 * HALO_M;        // 42 x 74
-template <bool DILATE> __device__ __forceinline__ uint8_t box3(const uint8_t* q, int stride) {
-    uint32_t r = q[0];
-#pragma unroll
-    for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-        for (int dx = -1; dx <= 1; dx++) r = DILATE ? max(r, (uint32_t)q[dy * stride + dx]) : min(r, (uint32_t)q[dy * stride + dx]);
-    return (uint8_t)r;
+// edges -> dilate -> erode -> dilate -> erode (3x3 box; pixels outside the image are ignored) on row masks, then the 3x3
+// Gaussian (taps 1 2 1, reflect-101) of the 0 / 255 result and the per-image maximum.  One warp per 54 x 22 tile (+5 halo).
+constexpr int MO_IW = 54, MO_IH = 22, MO_HALO = 5;
+__device__ __forceinline__ uint64_t dilate_rows(uint64_t e, int lane) { const uint64_t h = e | (e << 1) | (e >> 1); return h | shfl_up64(h, lane) | shfl_dn64(h, lane); }
+__device__ __forceinline__ uint64_t erode_rows(uint64_t e, int lane) {
+    const uint64_t h = e & (e << 1) & (e >> 1);
+    const uint64_t up = __shfl_up_sync(0xffffffffu, h, 1), dn = __shfl_down_sync(0xffffffffu, h, 1);
+    return h & (lane == 0 ? 0ull : up) & (lane == 31 ? 0ull : dn);
 }
 __global__ void __launch_bounds__(IT_THREADS)
-morph_kernel(const uint8_t* __restrict__ pmap, int H, int W, uint8_t* __restrict__ soft, unsigned int* __restrict__ maxv) {
-    __shared__ uint8_t sa[RM_H * RM_W], sb[RM_H * RM_W];
-    __shared__ unsigned int smax;
-    const int t = threadIdx.x, b = blockIdx.z;
-    const int x0 = blockIdx.x * TW - HALO_M, y0 = blockIdx.y * TH - HALO_M;
-    const uint8_t* gp = pmap + (size_t)b * H * W;
-    if (t == 0) smax = 0;
-    // edges = 255 where the map says 2; outside the image 0 (dilate ignores it)
-    for (int i = t; i < RM_H * RM_W; i += IT_THREADS) {
-        const int v = i / RM_W, u = i - v * RM_W, y = y0 + v, x = x0 + u;
-        sa[i] = (y >= 0 && y < H && x >= 0 && x < W && gp[(size_t)y * W + x] == 2) ? 255 : 0;
-    }
-    __syncthreads();
-    // four 3x3 steps, ping-pong; the value outside the image is the neutral element of the NEXT step (erode: 255, dilate: 0)
-    auto step = [&](const uint8_t* in, uint8_t* out, int shrink, bool dilate, uint8_t outside) {
-        const int hh = RM_H - 2 * shrink, ww = RM_W - 2 * shrink;
-        for (int i = t; i < hh * ww; i += IT_THREADS) {
-            const int v = i / ww + shrink, u = i % ww + shrink, y = y0 + v, x = x0 + u;
-            uint8_t r = outside;
-            if (y >= 0 && y < H && x >= 0 && x < W) r = dilate ? box3<true>(in + v * RM_W + u, RM_W) : box3<false>(in + v * RM_W + u, RM_W);
-            out[v * RM_W + u] = r;
+morph_kernel(const uint8_t* __restrict__ pmap, int H, int W, int tiles_x, int tiles_y, int ntiles, uint8_t* __restrict__ soft, unsigned int* __restrict__ maxv) {
+    __shared__ uint64_t rows[IT_THREADS / 32][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile = blockIdx.x * (IT_THREADS / 32) + warp;
+    if (tile >= ntiles) return;
+    const int per_img = tiles_x * tiles_y;
+    const int b = tile / per_img, r = tile - b * per_img, ty = r / tiles_x, tx = r - ty * tiles_x;
+    const int y0 = ty * MO_IH - MO_HALO, x0 = tx * MO_IW - MO_HALO;
+    const RowMasks m = load_rows(pmap + (size_t)b * H * W, H, W, x0, y0, lane);
+    const uint64_t V = m.valid;
+    uint64_t e = m.strong;                                   // edge pixels; 0 outside the image (dilate ignores it)
+    e = dilate_rows(e, lane) | ~V;                           // outside = 255: ignored by the erode that follows
+    e = erode_rows(e, lane) & V;
+    e = dilate_rows(e, lane) | ~V;
+    e = erode_rows(e, lane) & V;
+    rows[warp][lane] = e;
+    __syncwarp();
+    uint32_t mx = 0;
+    uint8_t* sp = soft + (size_t)b * H * W;
+    int cx[2][3];                                            // this lane's two columns: window-relative neighbour columns after reflect-101
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) cx[k][d] = clampi(reflect101(x0 + lane + 32 * k + d - 1, W), W) - x0;
+    for (int rr = MO_HALO; rr < MO_HALO + MO_IH; rr++) {
+        const int y = y0 + rr;
+        if (y >= H) break;
+        const uint64_t r0 = rows[warp][reflect101(y - 1, H) - y0], r1 = rows[warp][rr], r2 = rows[warp][reflect101(y + 1, H) - y0];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int c = lane + 32 * k, x = x0 + c;
+            if (c < MO_HALO || c >= MO_HALO + MO_IW || x >= W) continue;
+            const uint32_t a0 = (uint32_t)((r0 >> cx[k][0]) & 1) + 2u * (uint32_t)((r0 >> cx[k][1]) & 1) + (uint32_t)((r0 >> cx[k][2]) & 1);
+            const uint32_t a1 = (uint32_t)((r1 >> cx[k][0]) & 1) + 2u * (uint32_t)((r1 >> cx[k][1]) & 1) + (uint32_t)((r1 >> cx[k][2]) & 1);
+            const uint32_t a2 = (uint32_t)((r2 >> cx[k][0]) & 1) + 2u * (uint32_t)((r2 >> cx[k][1]) & 1) + (uint32_t)((r2 >> cx[k][2]) & 1);
+            const uint32_t v = (255u * (a0 + 2u * a1 + a2) + 8u) >> 4;     // Q8 taps 64 128 64 twice: (acc * 4096 + 2^15) >> 16
+            sp[(size_t)y * W + x] = (uint8_t)v;
+            mx = max(mx, v);
         }
-        __syncthreads();
-    };
-    step(sa, sb, 1, true, 255);
-    step(sb, sa, 2, false, 0);
-    step(sa, sb, 3, true, 255);
-    // last erode: its consumer is GaussianBlur (reflect-101) -> compute at the mirrored coordinate
-    {
-        const int hh = RM_H - 8, ww = RM_W - 8;
-        for (int i = t; i < hh * ww; i += IT_THREADS) {
-            const int v = i / ww + 4, u = i % ww + 4;
-            const int ym = clampi(reflect101(y0 + v, H), H) - y0, xm = clampi(reflect101(x0 + u, W), W) - x0;
-            sa[v * RM_W + u] = box3<false>(sb + ym * RM_W + xm, RM_W);
-        }
-        __syncthreads();
-    }
-    unsigned int mx = 0;
-    for (int i = t; i < TH * TW; i += IT_THREADS) {
-        const int v = i / TW + HALO_M, u = i % TW + HALO_M, y = y0 + v, x = x0 + u;
-        if (y >= H || x >= W) continue;
-        const uint8_t* q = sa + v * RM_W + u;
-        const uint32_t acc = (uint32_t)q[-RM_W - 1] + 2u * q[-RM_W] + q[-RM_W + 1] + 2u * q[-1] + 4u * q[0] + 2u * q[1] + q[RM_W - 1] + 2u * q[RM_W] + q[RM_W + 1];
-        const uint32_t r = (acc + 8u) >> 4;                       // taps 64 128 64 (Q8): (acc * 4096 + 2^15) >> 16
-        soft[((size_t)b * H + y) * W + x] = (uint8_t)r;
-        mx = max(mx, r);
     }
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((t & 31) == 0 && mx) atomicMax(&smax, mx);
-    __syncthreads();
-    if (t == 0 && smax) atomicMax(maxv + b, smax);
+    if (lane == 0 && mx) atomicMax(maxv + b, mx);
 }
 
 // rgb pipeline: CLAHE blend + Gaussian 3x3 sigma 0.5 (taps 27 202 27) per colour plane
@@ -449,6 +490,7 @@ __global__ void resize_coeff_kernel(int in_size, int out_size, int ksize, int32_
 
 // horizontal pass; grayscale: the source row is blended on the fly = addWeighted(clahe, 0.7, rescale(soft), 0.3)
 constexpr int HR_ROWS = 4;
+static_assert(HR_ROWS * 64 == IT_THREADS, "blend_hresize_kernel: 64 threads per staged row");
 __global__ void __launch_bounds__(IT_THREADS)
 blend_hresize_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ soft, const unsigned int* __restrict__ maxv, int planes_per_image,
                      int H, int W, int S, int ksize, const int32_t* __restrict__ bounds, const int32_t* __restrict__ kk, uint8_t* __restrict__ hp) {
@@ -458,35 +500,35 @@ blend_hresize_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ 
     const int t = threadIdx.x, pl = blockIdx.y;
     const int y0 = blockIdx.x * HR_ROWS;
     const uint8_t* ap = a + (size_t)pl * H * W;
+    const int rr = t >> 6, tx = t & 63, y = y0 + rr;                // 64 threads per staged row (HR_ROWS = 4)
     if (soft) {
         // (e.astype(float) / e.max() * 255).astype(uint8) (float64, truncation); unchanged when the maximum is 0
         const unsigned int mx = maxv[pl / planes_per_image];
         rescale[t] = mx ? (uint8_t)__double2int_rz(__dmul_rn(__ddiv_rn((double)t, (double)mx), 255.0)) : (uint8_t)t;
         __syncthreads();
-        const uint8_t* sp = soft + (size_t)pl * H * W;
-        for (int i = t; i < HR_ROWS * W; i += IT_THREADS) {
-            const int r = i / W, x = i - r * W, y = y0 + r;
-            if (y >= H) continue;
-            const float e = (float)rescale[sp[(size_t)y * W + x]];
-            // cv2.addWeighted: fma(a, 0.7f, round_f32(e * 0.3f)), round half to even, saturate
-            row[i] = sat_rint(__fmaf_rn((float)ap[(size_t)y * W + x], 0.7f, __fmul_rn(e, 0.3f)));
+        if (y < H) {
+            const uint8_t* sp = soft + ((size_t)pl * H + y) * W;
+            const uint8_t* cp = ap + (size_t)y * W;
+            for (int x = tx; x < W; x += 64) {
+                const float e = (float)rescale[sp[x]];
+                // cv2.addWeighted: fma(a, 0.7f, round_f32(e * 0.3f)), round half to even, saturate
+                row[rr * W + x] = sat_rint(__fmaf_rn((float)cp[x], 0.7f, __fmul_rn(e, 0.3f)));
+            }
         }
-    } else {
-        for (int i = t; i < HR_ROWS * W; i += IT_THREADS) {
-            const int r = i / W, x = i - r * W, y = y0 + r;
-            if (y < H) row[i] = ap[(size_t)y * W + x];
-        }
+    } else if (y < H) {
+        const uint8_t* cp = ap + (size_t)y * W;
+        for (int x = tx; x < W; x += 64) row[rr * W + x] = cp[x];
     }
     __syncthreads();
-    for (int i = t; i < HR_ROWS * S; i += IT_THREADS) {
-        const int r = i / S, xx = i - r * S, y = y0 + r;
-        if (y >= H) continue;
-        const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
-        const int32_t* k = kk + (size_t)xx * ksize;
-        int acc = 1 << 21;
-        for (int j = 0; j < n; j++) acc += (int)row[r * W + xmin + j] * k[j];
-        acc >>= 22;
-        hp[((size_t)pl * H + y) * S + xx] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+    if (y < H) {
+        for (int xx = tx; xx < S; xx += 64) {
+            const int xmin = bounds[2 * xx], n = bounds[2 * xx + 1];
+            const int32_t* k = kk + (size_t)xx * ksize;
+            int acc = 1 << 21;
+            for (int j = 0; j < n; j++) acc += (int)row[rr * W + xmin + j] * k[j];
+            acc >>= 22;
+            hp[((size_t)pl * H + y) * S + xx] = (uint8_t)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+        }
     }
 }
 
@@ -509,7 +551,7 @@ vresize_norm_kernel(const uint8_t* __restrict__ hp, int planes_per_image, int H,
     }
 }
 
-struct ITLayout { size_t plane, lut, clahe, pmap, soft, hpass, maxv, ctl, tile_live, xb, xk, yb, yk, total; int ksx, ksy, htx, hty; };
+struct ITLayout { size_t plane, lut, clahe, pmap, soft, hpass, maxv, ctl, dirty, zero_end, xb, xk, yb, yk, total; int ksx, ksy, htx, hty; };
 int resize_ksize(int in_size, int out_size) {
     const double scale = (double)in_size / out_size, fscale = scale < 1.0 ? 1.0 : scale;
     return (int)ceil(fscale) * 2 + 1;
@@ -522,8 +564,9 @@ ITLayout it_layout(int B, int H, int W, int planes, int tiles, int S) {
     L.plane = take(img); L.lut = take((size_t)B * planes * tiles * 256); L.clahe = take(img); L.pmap = take(img); L.soft = take(img);
     L.hpass = take((size_t)B * planes * H * S);
     L.maxv = take((size_t)B * 4); L.ctl = take(sizeof(HystCtl));
-    L.htx = (W + HT_W - 1) / HT_W; L.hty = (H + HT_H - 1) / HT_H;
-    L.tile_live = take((size_t)B * L.htx * L.hty);
+    L.htx = (W + HY_IW - 1) / HY_IW; L.hty = (H + HY_IH - 1) / HY_IH;
+    L.dirty = take((size_t)2 * B * L.htx * L.hty);
+    L.zero_end = off;                                          // [maxv, zero_end) is cleared before every run
     L.ksx = resize_ksize(W, S); L.ksy = resize_ksize(H, S);
     L.xb = take((size_t)S * 8); L.xk = take((size_t)S * L.ksx * 4); L.yb = take((size_t)S * 8); L.yk = take((size_t)S * L.ksy * 4);
     L.total = off;
@@ -575,7 +618,7 @@ extern "C" int kpd_itransform(const uint8_t* d_src, int batch, int height, int w
     p.lut_scale = 255.0f / (float)area;
     uint8_t* plane = (uint8_t*)(ws + L.plane); uint8_t* lut = (uint8_t*)(ws + L.lut); uint8_t* clahe = (uint8_t*)(ws + L.clahe);
     uint8_t* pmap = (uint8_t*)(ws + L.pmap); uint8_t* soft = (uint8_t*)(ws + L.soft); uint8_t* hp = (uint8_t*)(ws + L.hpass);
-    unsigned int* maxv = (unsigned int*)(ws + L.maxv); HystCtl* ctl = (HystCtl*)(ws + L.ctl); uint8_t* tile_live = (uint8_t*)(ws + L.tile_live);
+    unsigned int* maxv = (unsigned int*)(ws + L.maxv); HystCtl* ctl = (HystCtl*)(ws + L.ctl); uint8_t* dirty = (uint8_t*)(ws + L.dirty);
     int32_t* xb = (int32_t*)(ws + L.xb); int32_t* xk = (int32_t*)(ws + L.xk); int32_t* yb = (int32_t*)(ws + L.yb); int32_t* yk = (int32_t*)(ws + L.yk);
     ProfScope ps("itransform", s);
 
@@ -583,40 +626,49 @@ extern "C" int kpd_itransform(const uint8_t* d_src, int batch, int height, int w
     KPD_LAUNCH_CHECK();
     resize_coeff_kernel<<<(S + 127) / 128, 128, 0, s>>>(H, S, L.ksy, yb, yk);
     KPD_LAUNCH_CHECK();
+    { ProfScope pp("itransform.lut", s);
     clahe_lut_kernel<<<batch * planes * ntile, IT_THREADS, 0, s>>>(p, plane, lut);
-    KPD_LAUNCH_CHECK();
+    KPD_LAUNCH_CHECK(); }
     ClaheGeom g{tiles_x, tiles_y, 1.0f / (float)p.tw, 1.0f / (float)p.th};
     const dim3 tgrid((W + TW - 1) / TW, (H + TH - 1) / TH, batch * planes);
+    const dim3 cgrid((W + CT_W - 1) / CT_W, (H + CT_H - 1) / CT_H, batch * planes);
     const uint8_t* resize_src; const uint8_t* soft_arg = nullptr;
     if (grayscale) {
-        clahe_canny_kernel<<<tgrid, IT_THREADS, 0, s>>>(plane, lut, g, H, W, 100, 200, clahe, pmap);
-        KPD_LAUNCH_CHECK();
-        KPD_CUDA(cudaMemsetAsync(maxv, 0, L.tile_live - L.maxv, s));                   // per-image maxima + hysteresis control block
+        { ProfScope pp("itransform.clahe_canny", s);
+        clahe_canny_kernel<<<cgrid, IT_THREADS, 0, s>>>(plane, lut, g, H, W, 100, 200, clahe, pmap);
+        KPD_LAUNCH_CHECK(); }
+        KPD_CUDA(cudaMemsetAsync(maxv, 0, L.zero_end - L.maxv, s));                    // per-image maxima, hysteresis control block, dirty flags
         int dev = 0, sms = 0, per_sm = 0;
         KPD_CUDA(cudaGetDevice(&dev));
         KPD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         KPD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hysteresis_kernel, IT_THREADS, 0));
         const int ntiles = batch * L.htx * L.hty;
-        const int hgrid = std::max(1, std::min(ntiles, sms * std::min(per_sm, 4)));
+        const int hgrid = std::max(1, std::min((ntiles + IT_THREADS / 32 - 1) / (IT_THREADS / 32), sms * std::min(per_sm, 4)));
         int Bv = batch, Hv = H, Wv = W, htx = L.htx, hty = L.hty;
-        void* args[] = {&pmap, &Bv, &Hv, &Wv, &htx, &hty, &tile_live, &ctl};
+        void* args[] = {&pmap, &Bv, &Hv, &Wv, &htx, &hty, &dirty, &ctl};
+        { ProfScope pp("itransform.hysteresis", s);
         KPD_CUDA(cudaLaunchCooperativeKernel((const void*)hysteresis_kernel, dim3(hgrid), dim3(IT_THREADS), args, 0, s));
-        KPD_LAUNCH_CHECK();
-        morph_kernel<<<tgrid, IT_THREADS, 0, s>>>(pmap, H, W, soft, maxv);
-        KPD_LAUNCH_CHECK();
+        KPD_LAUNCH_CHECK(); }
+        const int mtx = (W + MO_IW - 1) / MO_IW, mty = (H + MO_IH - 1) / MO_IH, mtiles = batch * mtx * mty;
+        { ProfScope pp("itransform.morph", s);
+        morph_kernel<<<(mtiles + IT_THREADS / 32 - 1) / (IT_THREADS / 32), IT_THREADS, 0, s>>>(pmap, H, W, mtx, mty, mtiles, soft, maxv);
+        KPD_LAUNCH_CHECK(); }
         resize_src = clahe; soft_arg = soft;
     } else {
+        { ProfScope pp("itransform.clahe_gauss3", s);
         clahe_gauss3_kernel<<<tgrid, IT_THREADS, 0, s>>>(plane, lut, g, H, W, clahe);
-        KPD_LAUNCH_CHECK();
+        KPD_LAUNCH_CHECK(); }
         resize_src = clahe;
     }
     const size_t hsm = (size_t)HR_ROWS * W;
     KPD_CHECK_ARG(hsm <= 48 * 1024 - 512, "kpd_itransform: width %d too large for the row staging", W);
+    { ProfScope pp("itransform.hresize", s);
     blend_hresize_kernel<<<dim3((H + HR_ROWS - 1) / HR_ROWS, batch * planes), IT_THREADS, hsm, s>>>(resize_src, soft_arg, maxv, planes, H, W, S, L.ksx, xb, xk, hp);
-    KPD_LAUNCH_CHECK();
+    KPD_LAUNCH_CHECK(); }
     const float m[3] = {grayscale ? 0.5f : 0.485f, 0.456f, 0.406f}, sd[3] = {grayscale ? 0.5f : 0.229f, 0.224f, 0.225f};
+    { ProfScope pp("itransform.vresize", s);
     vresize_norm_kernel<<<dim3(std::max(1, std::min(64, (S * S + IT_THREADS - 1) / IT_THREADS)), batch * planes), IT_THREADS, 0, s>>>(
         hp, planes, H, S, L.ksy, yb, yk, m[0], m[1], m[2], sd[0], sd[1], sd[2], d_out);
-    KPD_LAUNCH_CHECK();
+    KPD_LAUNCH_CHECK(); }
     return 0;
 }
