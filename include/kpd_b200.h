@@ -196,6 +196,24 @@ int  kpd_itransform_stage_offsets(int batch, int height, int width, int grayscal
 int  kpd_itransform(const uint8_t* d_src, int batch, int height, int width, int channels, int grayscale, double clip_limit,
                     int tiles_x, int tiles_y, int out_size, float* d_out, void* d_scratch, void* stream);
 
+/* ---- generic fp32 layers ------------------------------------------------------------- */
+/* Shape-generic CUDA-core kernels behind the classes the reference exports but never instantiates (`BACKBONE`,
+ * dll/models/backbone.py:41-245; `KEYPOINT_HEAD`, dll/models/keypoint_head.py:9-90).  NHWC float32, exact fp32 FMA, fixed
+ * summation orders.  Activation codes: 0 none, 1 ReLU, 2 Hardswish, 3 Hardsigmoid, 4 sigmoid, 5 ReLU6.
+ * kpd_conv2d: d_out[n][oy][ox][co] = act2( act( conv(d_in * d_in_scale[n][ci]) + d_bias ) + d_residual ); d_w [k][k][cin/groups][cout];
+ *   d_bias, d_in_scale [n][cin], d_residual (shape of d_out) may be NULL.  BatchNorm is folded into d_w / d_bias by the caller.
+ * kpd_adaptive_avgpool: torch adaptive_avg_pool2d bins.  kpd_linear: d_y[m][n] = act(d_x[m][:] . d_w[n][:] + d_b[n]).
+ * kpd_layernorm: over the last dimension, biased variance.  kpd_mul_map: d_out[p][c] = d_x[p][c] * d_map[p].
+ * kpd_upsample_add: d_dst += nearest resize of d_src (F.interpolate(mode='nearest', size=...), backbone.py:35-37). */
+int  kpd_conv2d(const float* d_in, const float* d_w, const float* d_bias, const float* d_in_scale, const float* d_residual,
+                float* d_out, int n, int h, int w, int cin, int cout, int k, int stride, int pad, int groups, int act, int act2,
+                void* stream);
+int  kpd_adaptive_avgpool(const float* d_in, float* d_out, int n, int h, int w, int c, int oh, int ow, void* stream);
+int  kpd_linear(const float* d_x, const float* d_w, const float* d_b, float* d_y, int m, int k, int n, int act, void* stream);
+int  kpd_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, float eps, float* d_y, int m, int n, int act, void* stream);
+int  kpd_mul_map(const float* d_x, const float* d_map, float* d_out, int64_t pixels, int c, void* stream);
+int  kpd_upsample_add(float* d_dst, const float* d_src, int n, int h, int w, int hs, int ws, int c, void* stream);
+
 /* ---- misc ---------------------------------------------------------------------------------------- */
 const char* kpd_last_error(void);
 int  kpd_abi_version(void);

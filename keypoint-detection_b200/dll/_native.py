@@ -64,6 +64,12 @@ _SIGNATURES = {
     "kpd_itransform_scratch_bytes": (C.c_size_t, [C.c_int] * 7),
     "kpd_itransform_stage_offsets": (C.c_int, [C.c_int] * 7 + [C.POINTER(C.c_size_t)]),
     "kpd_itransform": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "kpd_conv2d": (C.c_int, [_P] * 6 + [C.c_int] * 11 + [_P]),
+    "kpd_adaptive_avgpool": (C.c_int, [_P, _P] + [C.c_int] * 6 + [_P]),
+    "kpd_linear": (C.c_int, [_P] * 4 + [C.c_int] * 4 + [_P]),
+    "kpd_layernorm": (C.c_int, [_P, _P, _P, C.c_float, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "kpd_mul_map": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P]),
+    "kpd_upsample_add": (C.c_int, [_P, _P] + [C.c_int] * 6 + [_P]),
     "kpd_last_error": (C.c_char_p, []),
     "kpd_abi_version": (C.c_int, []),
     "kpd_launch_count": (C.c_int64, [C.c_int]),

@@ -169,3 +169,29 @@ def synth_nms_candidates(images, m=100, seed=5):
     boxes = np.concatenate([c, s], axis=-1).astype(np.float32)
     scores = g.uniform(0, 1, (images, m)).astype(np.float32)
     return boxes, scores
+
+
+def synth_generic_state(shapes, seed=0):
+    """Deterministic non-trivial weights for an arbitrary module tree (SURVEY 8f N4 classes): `shapes` maps state_dict keys to
+    (shape, is_integer); values depend only on (key, shape, seed).  BatchNorm statistics are de-tuned so that folding matters."""
+    import zlib
+    out = {}
+    for key in sorted(shapes):
+        shape, is_int = shapes[key]
+        rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(key.encode())]))
+        leaf = key.rsplit(".", 1)[-1]
+        if is_int:
+            v = np.zeros(shape, np.int64)
+        elif leaf == "running_var":
+            v = rng.uniform(0.5, 1.5, shape)
+        elif leaf == "running_mean":
+            v = rng.normal(0, 0.2, shape)
+        elif leaf == "bias":
+            v = rng.normal(0, 0.1, shape)
+        elif len(shape) == 1:                                   # BatchNorm / LayerNorm scale
+            v = rng.uniform(0.7, 1.3, shape)
+        else:
+            fan_in = int(np.prod(shape[1:]))
+            v = rng.normal(0, np.sqrt(2.0 / fan_in), shape)
+        out[key] = v.astype(np.int64 if is_int else np.float32)
+    return out
