@@ -34,7 +34,7 @@ class ITransform:
         self.device = None if device is None else torch.device(device)
         if self.device is not None and self.device.type != "cuda":
             raise ValueError(f"ITransform(device=...) selects the CUDA pipeline; got {self.device} (omit it for the host path)")
-        self._scratch = {}
+        self._scratch, self._staging, self.h2d_chunks = {}, {}, 4
 
     # ---- CUDA pipeline (kpd_itransform)
     def batch(self, images, return_stages=False):
@@ -52,12 +52,14 @@ class ITransform:
             x = x.unsqueeze(-1)
         if x.dim() != 4 or x.shape[-1] not in (1, 3, 4):
             raise ValueError(f"ITransform.batch expects [B,H,W] or [B,H,W,C] with C in 1, 3, 4; got {tuple(x.shape)}")
-        x = x.to(dev, non_blocking=True).contiguous()
         B, H, W, Cn = x.shape
         S, gray = int(self.img_size), 1 if self.grayscale else 0
         tx, ty = int(self.tile_size[0]), int(self.tile_size[1])
         lib = _native.load()
-        geom = (B, H, W, gray, tx, ty, S)
+        # a pinned host batch is copied in chunks on a side stream so that chunk i + 1 crosses PCIe under chunk i's kernels
+        chunks = self.h2d_chunks if (not x.is_cuda and x.is_pinned() and x.is_contiguous() and B >= 2 * self.h2d_chunks and not return_stages) else 1
+        per = (B + chunks - 1) // chunks
+        geom = (per if chunks > 1 else B, H, W, gray, tx, ty, S)
         with torch.cuda.device(dev):
             need = lib.kpd_itransform_scratch_bytes(*geom)
             if need == 0:
@@ -66,6 +68,28 @@ class ITransform:
             if ws is None or ws.numel() < need:
                 ws = self._scratch[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
             out = torch.empty((B, 1 if gray else 3, S, S), dtype=torch.float32, device=dev)
+            cur = torch.cuda.current_stream(dev)
+            if chunks > 1:
+                st = self._staging.get(dev)
+                if st is None or st[0].numel() < x.numel():
+                    st = self._staging[dev] = (torch.empty(x.numel(), dtype=torch.uint8, device=dev), torch.cuda.Stream(dev), torch.cuda.Event())
+                buf, side, reuse = st
+                xd = buf[:x.numel()].view(x.shape)
+                side.wait_event(reuse)                                  # the previous call's kernels are done with the staging buffer
+                side.wait_stream(cur)
+                landed = []
+                with torch.cuda.stream(side):
+                    for lo in range(0, B, per):
+                        xd[lo:lo + per].copy_(x[lo:lo + per], non_blocking=True)
+                        e = torch.cuda.Event(); e.record(side); landed.append(e)
+                for i, lo in enumerate(range(0, B, per)):
+                    n = min(per, B - lo)
+                    cur.wait_event(landed[i])
+                    _native.check(lib.kpd_itransform(_native.ptr(xd[lo:lo + n]), n, H, W, Cn, gray, float(self.clip_limit), tx, ty, S,
+                                                     _native.ptr(out[lo:lo + n]), _native.ptr(ws), _native.stream_ptr(dev)), "kpd_itransform")
+                reuse.record(cur)
+                return out
+            x = x.to(dev, non_blocking=True).contiguous()
             _native.check(lib.kpd_itransform(_native.ptr(x), B, H, W, Cn, gray, float(self.clip_limit), tx, ty, S,
                                              _native.ptr(out), _native.ptr(ws), _native.stream_ptr(dev)), "kpd_itransform")
             if not return_stages:

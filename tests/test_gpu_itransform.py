@@ -97,6 +97,17 @@ def test_batch_independence_and_determinism_at_bench_size():
     assert torch.equal(a[5], a[13])                                            # same source image in another batch slot
 
 
+def test_pinned_host_batch_is_chunk_pipelined_and_identical():
+    imgs = torch.from_numpy(np.stack([O.synth_photo(120, 160, 60 + i) for i in range(10)]))
+    t = _t(224, 2.0, (8, 8), True)
+    resident = t.batch(imgs.cuda())
+    for _ in range(2):                                                         # second call reuses the staging buffer
+        piped = t.batch(imgs.pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(resident, piped)
+    assert torch.equal(resident, t.batch(imgs))                                # pageable host tensor: plain copy path
+
+
 def test_feeds_the_model():
     """ITransform(device='cuda') output goes straight into MultiPersonKeypointModel.predict (the predict.py path)."""
     from dll import MultiPersonKeypointModel
