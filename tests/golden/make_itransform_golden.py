@@ -13,8 +13,6 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, ROOT)
-sys.path.insert(0, "/root/reference")
 
 CASES = [  # (name, h, w, seed, channels, grayscale, img_size, clip_limit, tiles)
     ("g_240x320", 240, 320, 1, 3, True, 224, 1.5, (8, 8)),
@@ -28,6 +26,8 @@ CASES = [  # (name, h, w, seed, channels, grayscale, img_size, clip_limit, tiles
 
 
 def main():
+    sys.path.insert(0, ROOT)                       # for `oracle`; only when run as a script: the tests import this file for its tables
+    sys.path.insert(0, "/root/reference")          # the reference package (build container only)
     import cv2
     import PIL
     import torchvision

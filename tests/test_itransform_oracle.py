@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 from oracle import itransform as O                                             # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden", "itransform.npz")
