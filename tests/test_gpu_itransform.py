@@ -62,6 +62,16 @@ def test_every_stage_against_oracle(hw):
         assert np.array_equal(out[b].cpu().numpy(), O.to_tensor_normalize(O.pil_resize_bilinear(mixed, 224, 224))), (hw, b)
 
 
+def test_fine_clahe_grid():
+    """16x16 CLAHE tiles of 10x13 pixels: a 76-pixel Canny region blends between 8 x 7 tile LUTs."""
+    img = O.synth_photo(160, 208, 77)
+    out, st = _t(224, 3.0, (16, 16), True).batch(torch.from_numpy(img[None]), return_stages=True)
+    ref = {}
+    mixed = O.to_grayscale_clahe(img, 3.0, (16, 16), stages=ref)
+    assert np.array_equal(st["clahe"][0, 0].cpu().numpy(), ref["clahe"]) and np.array_equal(st["edges"][0, 0].cpu().numpy(), ref["edges"])
+    assert np.array_equal(out[0].cpu().numpy(), O.to_tensor_normalize(O.pil_resize_bilinear(mixed, 224, 224)))
+
+
 def test_rgb_pipeline_and_input_forms():
     img = O.synth_photo(150, 210, 31)
     t = _t(96, 1.5, (8, 8), False)
