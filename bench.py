@@ -494,16 +494,27 @@ def sub_pipeline(model, args, steps):
     t = ITransform(args.size, 2.0, (8, 8), True, device="cuda")
     kp_host, vis_host = torch.empty(B, 1, 1, 17, 2).pin_memory(), torch.empty(B, 1, 1, 17, 3).pin_memory()
 
+    state = {"ticket": t.prefetch(host)}
+
     def step():
+        ticket, state["ticket"] = state["ticket"], t.prefetch(host)      # the next step's frames start crossing PCIe now (second staging slot)
+        out = model.predict({"image": t.batch(ticket), "bboxes": boxes})
+        kp_host.copy_(out["keypoints"], non_blocking=True); vis_host.copy_(out["visibilities"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def step_serial():
         out = model.predict({"image": t.batch(host), "bboxes": boxes})
         kp_host.copy_(out["keypoints"], non_blocking=True); vis_host.copy_(out["visibilities"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(torch.cuda.current_device()).start()
     ms = ev_time(step, steps)
+    ms_serial = ev_time(step_serial, steps)
     clocks = sampler.stop()
     return {"workload": f"uint8 frames [{B},480,640,3] (pinned host) -> ITransform -> predict (P=1) -> keypoints/visibilities on the host",
-            "value": B / ms * 1e3, "unit": "images/sec", "ms_per_step": ms, "h2d_bytes_per_step": int(host.numel()) + B * 16,
+            "value": B / ms * 1e3, "unit": "images/sec", "ms_per_step": ms, "serial_call": {"value": B / ms_serial * 1e3, "ms_per_step": ms_serial},
+            "note": "every step copies its own frames from pinned host memory (prefetch of step i + 1 under step i's kernels) and reads its keypoints / visibilities back",
+            "h2d_bytes_per_step": int(host.numel()) + B * 16,
             "d2h_bytes_per_step": B * 17 * 5 * 4, "finite": bool(torch.isfinite(kp_host).all()), "clocks": clocks}
 
 

@@ -28,6 +28,13 @@ def _cv2():
     return cv2
 
 
+class _Prefetched:
+    """Ticket of `ITransform.prefetch`: the staged device view of a pinned host batch and the events of its chunked copy."""
+
+    def __init__(self, device_view, landed, per, reuse, host):
+        self.device_view, self.landed, self.per, self.reuse, self.host = device_view, landed, per, reuse, host
+
+
 class ITransform:
     def __init__(self, img_size=224, clip_limit=1.5, tile_size=(8, 8), grayscale=True, device=None):
         self.img_size, self.clip_limit, self.tile_size, self.grayscale = img_size, clip_limit, tuple(tile_size), grayscale
@@ -37,14 +44,7 @@ class ITransform:
         self._scratch, self._staging, self.h2d_chunks = {}, {}, 4
 
     # ---- CUDA pipeline (kpd_itransform)
-    def batch(self, images, return_stages=False):
-        """[B,H,W] / [B,H,W,C] uint8 tensor or array (C = 1, 3 or 4; host or device) -> float32 [B,C',S,S] on the device.
-        With return_stages=True also a dict of the intermediate uint8 planes (gray, clahe, edges, soft, hpass)."""
-        import ctypes as C
-        from .. import _native
-        if self.device is None:
-            raise RuntimeError("ITransform.batch needs ITransform(..., device='cuda')")
-        dev = _native.require_cuda(self.device)
+    def _check_images(self, images):
         x = torch.as_tensor(images)
         if x.dtype != torch.uint8:
             raise TypeError(f"ITransform.batch expects uint8 images, got {x.dtype}")
@@ -52,14 +52,61 @@ class ITransform:
             x = x.unsqueeze(-1)
         if x.dim() != 4 or x.shape[-1] not in (1, 3, 4):
             raise ValueError(f"ITransform.batch expects [B,H,W] or [B,H,W,C] with C in 1, 3, 4; got {tuple(x.shape)}")
+        return x
+
+    def prefetch(self, images):
+        """Start the host-to-device copy of a PINNED uint8 batch on the side stream (in `h2d_chunks` pieces) and return a ticket
+        for `batch()`.  Two staging slots per device: the copy of batch i + 1 can cross PCIe while batch i is still being
+        transformed and consumed, which is how an inference loop over camera frames hides the 0.9 MB per frame."""
+        from .. import _native
+        if self.device is None:
+            raise RuntimeError("ITransform.prefetch needs ITransform(..., device='cuda')")
+        dev = _native.require_cuda(self.device)
+        x = self._check_images(images)
+        if x.is_cuda or not x.is_pinned() or not x.is_contiguous():
+            raise ValueError("ITransform.prefetch expects a contiguous pinned host tensor")
+        B = x.shape[0]
+        chunks = max(1, min(self.h2d_chunks, B // 2))
+        per = (B + chunks - 1) // chunks
+        with torch.cuda.device(dev):
+            st = self._staging.setdefault(dev, {"side": torch.cuda.Stream(dev), "slots": [None, None], "next": 0})
+            k = st["next"]; st["next"] = k ^ 1
+            slot = st["slots"][k]
+            if slot is None or slot[0].numel() < x.numel():
+                slot = st["slots"][k] = (torch.empty(x.numel(), dtype=torch.uint8, device=dev), torch.cuda.Event())
+            buf, reuse = slot
+            side = st["side"]
+            xd = buf[:x.numel()].view(x.shape)
+            side.wait_event(reuse)                                  # the kernels of the batch that last used this slot are done
+            landed = []
+            with torch.cuda.stream(side):
+                for lo in range(0, B, per):
+                    xd[lo:lo + per].copy_(x[lo:lo + per], non_blocking=True)
+                    e = torch.cuda.Event(); e.record(side); landed.append(e)
+        return _Prefetched(xd, landed, per, reuse, x)
+
+    def batch(self, images, return_stages=False):
+        """[B,H,W] / [B,H,W,C] uint8 tensor or array (C = 1, 3 or 4; host or device), or a `prefetch()` ticket -> float32
+        [B,C',S,S] on the device.  A pinned host batch is prefetched in chunks so that chunk i + 1 crosses PCIe under chunk
+        i's kernels.  With return_stages=True also a dict of the intermediate uint8 planes (gray, clahe, edges, soft, hpass)."""
+        import ctypes as C
+        from .. import _native
+        if self.device is None:
+            raise RuntimeError("ITransform.batch needs ITransform(..., device='cuda')")
+        dev = _native.require_cuda(self.device)
+        ticket = images if isinstance(images, _Prefetched) else None
+        if ticket is None:
+            x = self._check_images(images)
+            if not x.is_cuda and x.is_pinned() and x.is_contiguous() and x.shape[0] >= 2 * self.h2d_chunks and not return_stages:
+                ticket = self.prefetch(x)
+        if ticket is not None:
+            x = ticket.device_view
         B, H, W, Cn = x.shape
         S, gray = int(self.img_size), 1 if self.grayscale else 0
         tx, ty = int(self.tile_size[0]), int(self.tile_size[1])
         lib = _native.load()
-        # a pinned host batch is copied in chunks on a side stream so that chunk i + 1 crosses PCIe under chunk i's kernels
-        chunks = self.h2d_chunks if (not x.is_cuda and x.is_pinned() and x.is_contiguous() and B >= 2 * self.h2d_chunks and not return_stages) else 1
-        per = (B + chunks - 1) // chunks
-        geom = (per if chunks > 1 else B, H, W, gray, tx, ty, S)
+        per = ticket.per if ticket is not None else B
+        geom = (min(per, B), H, W, gray, tx, ty, S)
         with torch.cuda.device(dev):
             need = lib.kpd_itransform_scratch_bytes(*geom)
             if need == 0:
@@ -69,25 +116,13 @@ class ITransform:
                 ws = self._scratch[dev] = torch.empty(need, dtype=torch.uint8, device=dev)
             out = torch.empty((B, 1 if gray else 3, S, S), dtype=torch.float32, device=dev)
             cur = torch.cuda.current_stream(dev)
-            if chunks > 1:
-                st = self._staging.get(dev)
-                if st is None or st[0].numel() < x.numel():
-                    st = self._staging[dev] = (torch.empty(x.numel(), dtype=torch.uint8, device=dev), torch.cuda.Stream(dev), torch.cuda.Event())
-                buf, side, reuse = st
-                xd = buf[:x.numel()].view(x.shape)
-                side.wait_event(reuse)                                  # the previous call's kernels are done with the staging buffer
-                side.wait_stream(cur)
-                landed = []
-                with torch.cuda.stream(side):
-                    for lo in range(0, B, per):
-                        xd[lo:lo + per].copy_(x[lo:lo + per], non_blocking=True)
-                        e = torch.cuda.Event(); e.record(side); landed.append(e)
+            if ticket is not None:
                 for i, lo in enumerate(range(0, B, per)):
                     n = min(per, B - lo)
-                    cur.wait_event(landed[i])
-                    _native.check(lib.kpd_itransform(_native.ptr(xd[lo:lo + n]), n, H, W, Cn, gray, float(self.clip_limit), tx, ty, S,
+                    cur.wait_event(ticket.landed[i])
+                    _native.check(lib.kpd_itransform(_native.ptr(x[lo:lo + n]), n, H, W, Cn, gray, float(self.clip_limit), tx, ty, S,
                                                      _native.ptr(out[lo:lo + n]), _native.ptr(ws), _native.stream_ptr(dev)), "kpd_itransform")
-                reuse.record(cur)
+                ticket.reuse.record(cur)
                 return out
             x = x.to(dev, non_blocking=True).contiguous()
             _native.check(lib.kpd_itransform(_native.ptr(x), B, H, W, Cn, gray, float(self.clip_limit), tx, ty, S,

@@ -116,6 +116,16 @@ def test_pinned_host_batch_is_chunk_pipelined_and_identical():
     torch.cuda.synchronize()
     assert torch.equal(resident, piped)
     assert torch.equal(resident, t.batch(imgs))                                # pageable host tensor: plain copy path
+    # explicit tickets: two batches in flight (both staging slots), consumed in order
+    other = torch.from_numpy(np.stack([O.synth_photo(120, 160, 80 + i) for i in range(10)])).pin_memory()
+    t1, t2 = t.prefetch(imgs.pin_memory()), t.prefetch(other)
+    a, b = t.batch(t1), t.batch(t2)
+    t3 = t.prefetch(imgs.pin_memory())                                         # re-uses the first slot after its consumer
+    c = t.batch(t3)
+    torch.cuda.synchronize()
+    assert torch.equal(a, resident) and torch.equal(c, resident) and torch.equal(b, t.batch(other.cuda()))
+    with pytest.raises(ValueError):
+        t.prefetch(imgs)                                                       # not pinned
 
 
 def test_feeds_the_model():
