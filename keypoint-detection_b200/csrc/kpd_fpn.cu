@@ -33,10 +33,16 @@ __global__ void __launch_bounds__(128) pool_final_kernel(const float* __restrict
                                                          float* __restrict__ mx, int HW, int parts) {
     const int b = blockIdx.x, c = threadIdx.x;
     float s = 0.f, m = -INFINITY;
-    for (int i = 0; i < parts; i++) {
-        const float* o = part + (((int64_t)b * parts + i) * 2) * 128;
-        s += o[c]; m = fmaxf(m, o[128 + c]);
+    const float* o = part + ((int64_t)b * parts * 2) * 128 + c;
+    int i = 0;
+    for (; i + 8 <= parts; i += 8) {               // 16 loads in flight, then the sums in the canonical order (same bits as a serial loop)
+        float sv[8], mv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { sv[j] = __ldg(o + (size_t)(i + j) * 256); mv[j] = __ldg(o + (size_t)(i + j) * 256 + 128); }
+#pragma unroll
+        for (int j = 0; j < 8; j++) { s += sv[j]; m = fmaxf(m, mv[j]); }
     }
+    for (; i < parts; i++) { s += __ldg(o + (size_t)i * 256); m = fmaxf(m, __ldg(o + (size_t)i * 256 + 128)); }
     avg[(int64_t)b * 128 + c] = s / (float)HW;
     mx[(int64_t)b * 128 + c] = m;
 }

@@ -177,6 +177,91 @@ __global__ void __launch_bounds__(PF_THREADS, (R * NT <= 24) ? 3 : 2) pw_ffma_ke
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// Pixel-per-thread variant for the layers whose GEMM is too shallow for the tiled kernel above (K <= 96 with N <= 24: the
+// projections of features.1 / features.3; 49 -> 35 us and 56 -> 50 us at B = 256): the tiled kernel spends more
+// issue slots on its per-item prologue / epilogue than on 6..22 k-steps, and its lane-per-row float4 stores are 32 half-empty
+// sector writes per instruction.  Here a thread owns NPT output channels of one pixel (N / NPT threads per pixel), the weights sit in
+// shared memory (one broadcast LDS.128 per 4 FMAs), the pixel's K inputs come as float4 through L1, and the warp's outputs --
+// contiguous in memory -- leave through a padded shared-memory transposition as full 512-byte rows.  Accumulation order
+// (bias first, k ascending, SE factor applied to the input) is that of the tiled kernel: the results are bit-identical.
+template <int NPT>
+__global__ void __launch_bounds__(256) pw_px_kernel(const PwMma p) {
+    extern __shared__ __align__(16) float px_smem[];           // W [K][N / NPT][NPT + 4] | staging [8 warps][32][NPT + 4]
+    constexpr int LDS_ = NPT + 4;                              // padded chunk / row pitch: the N / NPT chunk addresses of one LDS.128 fall into different banks
+    const int K = p.K, N = p.N, tpp = N / NPT;
+    float* Ws = px_smem;
+    float* stg = px_smem + K * tpp * LDS_ + (threadIdx.x >> 5) * (32 * LDS_);
+    for (int i = threadIdx.x; i < K * N / 4; i += 256) {
+        const int k = i / (N / 4), rem = i - k * (N / 4), ch = rem / (NPT / 4), q = rem - ch * (NPT / 4);
+        *reinterpret_cast<float4*>(Ws + (k * tpp + ch) * LDS_ + q * 4) = __ldg(reinterpret_cast<const float4*>(p.Wraw) + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t total = p.M * tpp;                            // one thread per (pixel, channel chunk)
+    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + (threadIdx.x & ~31));
+    if (warp0 >= total) return;
+    const int64_t gt = warp0 + lane;
+    const bool live = gt < total;
+    const int64_t m = live ? gt / tpp : p.M - 1;
+    const int ch = live ? (int)(gt - m * tpp) : 0, n0 = ch * NPT;
+    float acc[NPT];
+#pragma unroll
+    for (int c4 = 0; c4 < NPT / 4; c4++) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + c4);
+        acc[c4 * 4] = bv.x; acc[c4 * 4 + 1] = bv.y; acc[c4 * 4 + 2] = bv.z; acc[c4 * 4 + 3] = bv.w;
+    }
+    const float4* ap = reinterpret_cast<const float4*>(p.A + (size_t)m * K);
+    const float4* sp = p.se_scale ? reinterpret_cast<const float4*>(p.se_scale + (size_t)(m / p.hw) * K) : nullptr;
+#pragma unroll 2
+    for (int k4 = 0; k4 < K / 4; k4++) {
+        float4 a = __ldg(ap + k4);
+        if (sp) { const float4 sc = __ldg(sp + k4); a.x *= sc.x; a.y *= sc.y; a.z *= sc.z; a.w *= sc.w; }
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            const float av = kk == 0 ? a.x : kk == 1 ? a.y : kk == 2 ? a.z : a.w;
+            const float4* wr = reinterpret_cast<const float4*>(Ws + ((k4 * 4 + kk) * tpp + ch) * LDS_);
+#pragma unroll
+            for (int c4 = 0; c4 < NPT / 4; c4++) {
+                const float4 w = wr[c4];
+                acc[c4 * 4] = fmaf(av, w.x, acc[c4 * 4]); acc[c4 * 4 + 1] = fmaf(av, w.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(av, w.z, acc[c4 * 4 + 2]); acc[c4 * 4 + 3] = fmaf(av, w.w, acc[c4 * 4 + 3]);
+            }
+        }
+    }
+    const float* resp = nullptr;
+    if (p.res_mode == 1) resp = p.res + (size_t)m * N + n0;
+    else if (p.res_mode == 2) {
+        const uint32_t r = (uint32_t)m, row = r / (uint32_t)p.W, x = r - row * p.W, b = row / (uint32_t)p.H, y = row - b * p.H;
+        resp = p.res + ((size_t)(b * (p.H / p.up) + y / p.up) * (p.W / p.up) + x / p.up) * N + n0;
+    }
+#pragma unroll
+    for (int c4 = 0; c4 < NPT / 4; c4++) {
+        float4 v = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+        if (p.act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        else if (p.act == ACT_HSWISH) { ActHswish h; v.x = h(v.x); v.y = h(v.y); v.z = h(v.z); v.w = h(v.w); }
+        if (resp) { const float4 q = __ldg(reinterpret_cast<const float4*>(resp) + c4); v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w; }
+        if (p.round_tf32) { v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w); }
+        *reinterpret_cast<float4*>(stg + lane * LDS_ + c4 * 4) = v;
+    }
+    __syncwarp();
+    // the warp's 32 x NPT outputs are one contiguous run of `out`: store it in memory order, 512 bytes per instruction
+    float4* op = reinterpret_cast<float4*>(p.out) + warp0 * (NPT / 4);
+    const int64_t lim = (total - warp0 < 32 ? total - warp0 : 32) * (NPT / 4);
+#pragma unroll
+    for (int j = 0; j < NPT / 4; j++) {
+        const int e = j * 32 + lane, src_lane = e / (NPT / 4), q = e - src_lane * (NPT / 4);
+        if (e < lim) op[e] = *reinterpret_cast<const float4*>(stg + src_lane * LDS_ + q * 4);
+    }
+}
+
+static int px_npt(const PwMma& p) {             // channels per thread of the pixel-per-thread kernel, 0 = not eligible
+    if (p.out2 || (p.K & 3) || p.K > 96) return 0;
+    if (p.N == 16 || p.N == 24) return p.N;
+    // (N = 128 as 4 threads x 32 channels per pixel -- the K = 24 lateral -- measured 114 us against 95-103 us for the tiled kernel: not taken)
+    return 0;
+}
+
 // (R, NT, chunks) per layer: minimise chunks * (K/4 * cycles per 4-k step + per-item overhead), the step cost being the
 // larger of the shared-memory wavefronts 8*(4R+NT) and the per-sub-partition issue slots 2*(4*R*NT+R+NT); every extra
 // column chunk re-streams the A tile and pays the item prologue / epilogue again (~1500 issue cycles); items run in waves
@@ -205,6 +290,18 @@ int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s) {
     if (!p.Wraw) { set_error("pointwise_ffma: missing weights"); return KPD_ERR_ARG; }
     if (p.M <= 0) return 0;
     if (p.M >= ((int64_t)1 << 31) - PF_BM) { set_error("pointwise_ffma: M = %lld pixels exceeds the 32-bit pixel index", (long long)p.M); return KPD_ERR_UNSUPPORTED; }
+    if (const int npt = px_npt(p)) {
+        const int64_t threads = p.M * (p.N / npt);
+        const size_t smem = sizeof(float) * ((size_t)p.K * (p.N / npt) * (npt + 4) + 8 * 32 * (npt + 4));
+        const int grid = (int)((threads + 255) / 256);
+        constexpr int PX_SMEM_MAX = 96 * 1024;          // the attribute is set once per device: K <= 96, N <= 128 always fit
+        static uint64_t px_attr[3] = {};
+        if (npt == 16) { KPD_CUDA(ensure_smem_attr(pw_px_kernel<16>, PX_SMEM_MAX, px_attr[0])); pw_px_kernel<16><<<grid, 256, smem, s>>>(p); }
+        else if (npt == 24) { KPD_CUDA(ensure_smem_attr(pw_px_kernel<24>, PX_SMEM_MAX, px_attr[1])); pw_px_kernel<24><<<grid, 256, smem, s>>>(p); }
+        else { KPD_CUDA(ensure_smem_attr(pw_px_kernel<32>, PX_SMEM_MAX, px_attr[2])); pw_px_kernel<32><<<grid, 256, smem, s>>>(p); }
+        KPD_LAUNCH_CHECK();
+        return 0;
+    }
     const int tiles_m = (int)((p.M + PF_BM - 1) / PF_BM);
     const PfCfg c = choose_pf_cfg(p.K, p.N, tiles_m, sm_count);
     const int cover = 2 * c.R * c.NT;

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) head_att_maps_kernel(const float* __restr
 }
 
 template <typename OutT>
-__global__ void __launch_bounds__(256) head_att_apply_kernel(const float* __restrict__ roi_feat, const float* __restrict__ maps,
+__global__ void __launch_bounds__(256, 4) head_att_apply_kernel(const float* __restrict__ roi_feat, const float* __restrict__ maps,
                                                              const int32_t* __restrict__ roi_count, const float* __restrict__ cw_g,
                                                              const float* __restrict__ saw, const float* __restrict__ sab,
                                                              float* __restrict__ out_sw, OutT* __restrict__ out, int round_tf32) {
