@@ -72,6 +72,25 @@ def test_fine_clahe_grid():
     assert np.array_equal(out[0].cpu().numpy(), O.to_tensor_normalize(O.pil_resize_bilinear(mixed, 224, 224)))
 
 
+def test_random_geometries():
+    """Seeded sweep over image sizes (odd, prime, barely above the 16-pixel minimum, full HD), CLAHE grids that do / do not divide
+    them, clip limits (0 = plain histogram equalisation) and output sizes (down- and up-sampling): final tensor bit-exact."""
+    rng = np.random.default_rng(2024)
+    cases = [(16, 16, (2, 2), 1.5, 32), (17, 401, (3, 8), 2.0, 224), (1080, 1920, (8, 8), 2.0, 224), (611, 389, (7, 5), 0.0, 96),
+             (224, 224, (8, 8), 1.5, 224), (100, 100, (8, 8), 40.0, 300)]
+    for _ in range(6):
+        cases.append((int(rng.integers(20, 400)), int(rng.integers(20, 400)), (int(rng.integers(1, 9)), int(rng.integers(1, 9))),
+                      float(rng.choice([0.0, 1.0, 1.5, 2.0, 4.0])), int(rng.choice([64, 128, 224]))))
+    for k, (h, w, tiles, clip, size) in enumerate(cases):
+        img = O.synth_photo(h, w, 300 + k) if k % 3 else rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got = _t(size, clip, tiles, True)(img).cpu().numpy()
+        assert np.array_equal(got, O.itransform(img, size, clip, tiles)), (h, w, tiles, clip, size)
+    for k, (h, w, tiles, clip, size) in enumerate(cases[:2] + cases[3:8]):
+        img = O.synth_photo(h, w, 400 + k)
+        got = _t(size, clip, tiles, False)(img).cpu().numpy()
+        assert np.array_equal(got, O.itransform(img, size, clip, tiles, grayscale=False)), ("rgb", h, w, tiles, clip, size)
+
+
 def test_rgb_pipeline_and_input_forms():
     img = O.synth_photo(150, 210, 31)
     t = _t(96, 1.5, (8, 8), False)
