@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: 256 at N=1, 4096/N at N>1)")
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--persons", type=int, default=1)
-    ap.add_argument("--sub", default=None, help="comma list of sub-records at N=1: fp32,c4,c5,itransform,pipeline (default all; '' = none)")
+    ap.add_argument("--sub", default=None, help="comma list of sub-records at N=1: fp32,c4,c5,itransform,pipeline,small (default all; '' = none)")
     ap.add_argument("--it-batch", type=int, default=256)
     ap.add_argument("--c4-instances", type=int, default=65536)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
@@ -518,6 +518,27 @@ def sub_pipeline(model, args, steps):
             "d2h_bytes_per_step": B * 17 * 5 * 4, "finite": bool(torch.isfinite(kp_host).all()), "clocks": clocks}
 
 
+def sub_small_batch(model, args):
+    """Latency at serving batch sizes (BASELINE config[0] is B = 8): one blocking predict() per step against the same forward
+    replayed from a CUDA graph (model.capture); inputs resident, wall clock around synchronised calls."""
+    out = {"workload": "1x224x224, P=1, resident inputs; ms per forward, eager launches vs CUDA-graph replay"}
+    for B in (1, 8, 32):
+        x, b = make_inputs(B, args.size, 1)
+        batch = {"image": x.cuda(), "bboxes": b.cuda()}
+        captured = model.capture(batch)
+        for _ in range(5):
+            model.predict(batch); captured()
+        def wall(fn, n=200):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / n * 1e3
+        e, g = wall(lambda: model.predict(batch)), wall(captured)
+        out[f"B{B}"] = {"eager_ms": e, "graph_ms": g, "graph_images_per_s": B / g * 1e3}
+    return out
+
+
 def sub_c5(model, lib, args, pk, dev, steps):
     """BASELINE config C5: B=128 images of 512x512 with P=3 seeded boxes through the model, the person heads (1x1 box/cls
     convs, person_head.py:27-34) on the resulting FPN-0 map, and NMS (person_head.py:96-139) over 128 x 100 seeded candidates."""
@@ -691,7 +712,7 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
-    subs_wanted = (args.sub if args.sub is not None else ("fp32,c4,c5,itransform,pipeline" if world == 1 else "")).split(",")
+    subs_wanted = (args.sub if args.sub is not None else ("fp32,c4,c5,itransform,pipeline,small" if world == 1 else "")).split(",")
     subs_wanted = [s for s in subs_wanted if s]
     tf32_peak = measure_tf32_peak() if (world == 1) else None
     ms_step = ms / args.steps
@@ -740,6 +761,8 @@ def main():
         sub["c5"] = sub_c5(model, lib, args, pk, dev, steps_sub)
     if "itransform" in subs_wanted:
         sub["itransform"] = sub_itransform(lib, args, pk, steps_sub)
+    if "small" in subs_wanted:
+        sub["small_batch"] = sub_small_batch(model, args)
     if "pipeline" in subs_wanted:
         sub["pipeline"] = sub_pipeline(model, args, steps_sub)
     if "c4" in subs_wanted:

@@ -641,3 +641,20 @@ def test_detector_path_new_semantics(model, sd):
         assert torch.equal(none["visibilities"][:, 0, 0].cpu(), torch.tensor([[1.0, 0.0, 0.0]]).repeat(B, 17, 1))
     finally:
         det.conf_threshold = old
+
+
+def test_cuda_graph_capture_is_bit_identical(model):
+    """model.capture(): the whole forward replayed from a CUDA graph on new inputs of the captured shape."""
+    prev = model.precision
+    model.set_precision("bf16")
+    x0 = torch.from_numpy(synth_images(8, 1, 224, seed=5)).cuda(); b0 = torch.from_numpy(synth_boxes(8, 2, seed=6)).cuda()
+    x1 = torch.from_numpy(synth_images(8, 1, 224, seed=7)).cuda(); b1 = torch.from_numpy(synth_boxes(8, 2, seed=8, zero_slots=((3, 1),))).cuda()
+    captured = model.capture({"image": x0, "bboxes": b0})
+    for x, b in ((x1, b1), (x0, b0)):
+        ref = model.predict({"image": x, "bboxes": b})
+        ref = {k: ref[k].clone() for k in ("heatmap", "keypoints", "visibilities")}
+        out = captured(x, b)
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    model.set_precision(prev)
