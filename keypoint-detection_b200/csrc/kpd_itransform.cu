@@ -277,26 +277,30 @@ clahe_canny_kernel(const uint8_t* __restrict__ gray, const uint8_t* __restrict__
 // Hysteresis and the morphology chain work on binary images: a warp owns a 64 x 32 window as one 64-bit mask per row
 // (lane r = row r), so a 3x3 step over 2048 pixels is a handful of shifts, logic ops and two lane shuffles.
 struct RowMasks { uint64_t strong, cand, valid; };      // map == 2, map == 0, inside the image
+// Lane r reads its own row: 64 bytes as 17 aligned words re-aligned by funnel shifts; the map holds only 0 / 1 / 2, so "strong" is
+// bit 1 of a byte and "candidate" is both low bits clear; four byte flags are gathered into a nibble by one multiply.
+// (Words may start up to 3 bytes before / end up to 3 bytes after the window: still inside the scratch planes; masked by `valid`.)
 __device__ __forceinline__ RowMasks load_rows(const uint8_t* __restrict__ gp, int H, int W, int x0, int y0, int lane) {
     RowMasks m{0, 0, 0};
-    const int xa = x0 + lane, xb = xa + 32;
-    const bool ina = xa >= 0 && xa < W, inb = xb >= 0 && xb < W;
-#pragma unroll 4
-    for (int r = 0; r < 32; r++) {
-        const int y = y0 + r;
-        const bool iny = y >= 0 && y < H;
-        uint32_t pa = 1, pb = 1;
-        if (iny && ina) pa = __ldcg(gp + (size_t)y * W + xa);
-        if (iny && inb) pb = __ldcg(gp + (size_t)y * W + xb);
-        const uint32_t s_lo = __ballot_sync(0xffffffffu, pa == 2), s_hi = __ballot_sync(0xffffffffu, pb == 2);
-        const uint32_t c_lo = __ballot_sync(0xffffffffu, pa == 0), c_hi = __ballot_sync(0xffffffffu, pb == 0);
-        const uint32_t v_lo = __ballot_sync(0xffffffffu, iny && ina), v_hi = __ballot_sync(0xffffffffu, iny && inb);
-        if (lane == r) {
-            m.strong = (uint64_t)s_lo | ((uint64_t)s_hi << 32);
-            m.cand = (uint64_t)c_lo | ((uint64_t)c_hi << 32);
-            m.valid = (uint64_t)v_lo | ((uint64_t)v_hi << 32);
-        }
+    const int y = y0 + lane;
+    const int lo = max(0, -x0), hi = min(64, W - x0);                      // window columns inside the image: [lo, hi)
+    if (y < 0 || y >= H || hi <= lo) return m;
+    m.valid = ((hi - lo) == 64 ? ~0ull : ((1ull << (hi - lo)) - 1ull)) << lo;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(gp) + (size_t)y * W + x0;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(addr & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(addr & 3) * 8u;
+    uint32_t prev = __ldcg(wp);
+    uint64_t strong = 0, cand = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t next = __ldcg(wp + j + 1);
+        const uint32_t w = __funnelshift_r(prev, next, sh);               // window bytes 4j .. 4j+3
+        prev = next;
+        const uint32_t f2 = (w >> 1) & 0x01010101u, f0 = ~(w | (w >> 1)) & 0x01010101u;
+        strong |= (uint64_t)((f2 * 0x01020408u) >> 24) << (4 * j);        // byte flags at bits 0, 8, 16, 24 -> bits 24..27
+        cand |= (uint64_t)((f0 * 0x01020408u) >> 24) << (4 * j);
     }
+    m.strong = strong & m.valid; m.cand = cand & m.valid;
     return m;
 }
 __device__ __forceinline__ uint64_t shfl_up64(uint64_t v, int lane) { const uint64_t r = __shfl_up_sync(0xffffffffu, v, 1); return lane == 0 ? 0ull : r; }
@@ -386,7 +390,7 @@ __device__ __forceinline__ uint64_t erode_rows(uint64_t e, int lane) {
 }
 __global__ void __launch_bounds__(IT_THREADS)
 morph_kernel(const uint8_t* __restrict__ pmap, int H, int W, int tiles_x, int tiles_y, int ntiles, uint8_t* __restrict__ soft, unsigned int* __restrict__ maxv) {
-    __shared__ uint64_t rows[IT_THREADS / 32][32];
+    __shared__ uint64_t rows[IT_THREADS / 32][5][32];        // per warp: the 5 bit planes of the blurred rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile = blockIdx.x * (IT_THREADS / 32) + warp;
     if (tile >= ntiles) return;
@@ -400,28 +404,40 @@ morph_kernel(const uint8_t* __restrict__ pmap, int H, int W, int tiles_x, int ti
     e = erode_rows(e, lane) & V;
     e = dilate_rows(e, lane) | ~V;
     e = erode_rows(e, lane) & V;
-    rows[warp][lane] = e;
+    // 3x3 Gaussian (taps 1 2 1 per axis, reflect-101) of the 0 / 255 result as bit-sliced arithmetic on the row masks:
+    // per row h = left + 2 centre + right (3 bit planes), then v = h_up + 2 h + h_down (5 bit planes, 0..16), 64 columns at a time.
+    const int y = y0 + lane;
+    uint64_t L = e << 1, R = e >> 1;                         // left / right neighbour of every column
+    if (x0 <= 0 && -x0 < 64) { const int c = -x0; L = (L & ~(1ull << c)) | (((e >> (c + 1)) & 1ull) << c); }                // x = 0: its left neighbour is x = 1
+    if (W - 1 - x0 >= 1 && W - 1 - x0 < 64) { const int c = W - 1 - x0; R = (R & ~(1ull << c)) | (((e >> (c - 1)) & 1ull) << c); }   // x = W-1: its right neighbour is x = W-2
+    const uint64_t k = L & R, h0 = L ^ R, h1 = k ^ e, h2 = k & e;
+    uint64_t u0 = __shfl_up_sync(0xffffffffu, h0, 1), u1 = __shfl_up_sync(0xffffffffu, h1, 1), u2 = __shfl_up_sync(0xffffffffu, h2, 1);
+    uint64_t d0 = __shfl_down_sync(0xffffffffu, h0, 1), d1 = __shfl_down_sync(0xffffffffu, h1, 1), d2 = __shfl_down_sync(0xffffffffu, h2, 1);
+    if (y == 0) { u0 = d0; u1 = d1; u2 = d2; }               // reflect-101: the row above row 0 is row 1
+    if (y == H - 1) { d0 = u0; d1 = u1; d2 = u2; }           // the row below row H-1 is row H-2
+    const uint64_t t0 = u0 ^ d0, c0 = u0 & d0;
+    const uint64_t t1 = u1 ^ d1 ^ c0, c1 = (u1 & d1) | (c0 & (u1 ^ d1));
+    const uint64_t t2 = u2 ^ d2 ^ c1, t3 = (u2 & d2) | (c1 & (u2 ^ d2));
+    const uint64_t v1 = t1 ^ h0, e1 = t1 & h0;
+    const uint64_t v2 = t2 ^ h1 ^ e1, e2 = (t2 & h1) | (e1 & (t2 ^ h1));
+    const uint64_t v3 = t3 ^ h2 ^ e2, v4 = (t3 & h2) | (e2 & (t3 ^ h2));
+    uint64_t* pr = &rows[warp][0][0];
+    pr[0 * 32 + lane] = t0; pr[1 * 32 + lane] = v1; pr[2 * 32 + lane] = v2; pr[3 * 32 + lane] = v3; pr[4 * 32 + lane] = v4;
     __syncwarp();
     uint32_t mx = 0;
     uint8_t* sp = soft + (size_t)b * H * W;
-    int cx[2][3];                                            // this lane's two columns: window-relative neighbour columns after reflect-101
-#pragma unroll
-    for (int k = 0; k < 2; k++)
-#pragma unroll
-        for (int d = 0; d < 3; d++) cx[k][d] = clampi(reflect101(x0 + lane + 32 * k + d - 1, W), W) - x0;
     for (int rr = MO_HALO; rr < MO_HALO + MO_IH; rr++) {
-        const int y = y0 + rr;
-        if (y >= H) break;
-        const uint64_t r0 = rows[warp][reflect101(y - 1, H) - y0], r1 = rows[warp][rr], r2 = rows[warp][reflect101(y + 1, H) - y0];
+        const int yr = y0 + rr;
+        if (yr >= H) break;
+        const uint64_t p0 = pr[rr], p1 = pr[32 + rr], p2 = pr[64 + rr], p3 = pr[96 + rr], p4 = pr[128 + rr];
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int c = lane + 32 * k, x = x0 + c;
+        for (int kk = 0; kk < 2; kk++) {
+            const int c = lane + 32 * kk, x = x0 + c;
             if (c < MO_HALO || c >= MO_HALO + MO_IW || x >= W) continue;
-            const uint32_t a0 = (uint32_t)((r0 >> cx[k][0]) & 1) + 2u * (uint32_t)((r0 >> cx[k][1]) & 1) + (uint32_t)((r0 >> cx[k][2]) & 1);
-            const uint32_t a1 = (uint32_t)((r1 >> cx[k][0]) & 1) + 2u * (uint32_t)((r1 >> cx[k][1]) & 1) + (uint32_t)((r1 >> cx[k][2]) & 1);
-            const uint32_t a2 = (uint32_t)((r2 >> cx[k][0]) & 1) + 2u * (uint32_t)((r2 >> cx[k][1]) & 1) + (uint32_t)((r2 >> cx[k][2]) & 1);
-            const uint32_t v = (255u * (a0 + 2u * a1 + a2) + 8u) >> 4;     // Q8 taps 64 128 64 twice: (acc * 4096 + 2^15) >> 16
-            sp[(size_t)y * W + x] = (uint8_t)v;
+            const uint32_t acc = (uint32_t)((p0 >> c) & 1) | ((uint32_t)((p1 >> c) & 1) << 1) | ((uint32_t)((p2 >> c) & 1) << 2) |
+                                 ((uint32_t)((p3 >> c) & 1) << 3) | ((uint32_t)((p4 >> c) & 1) << 4);
+            const uint32_t v = (255u * acc + 8u) >> 4;                     // Q8 taps 64 128 64 twice: (acc * 4096 + 2^15) >> 16
+            sp[(size_t)yr * W + x] = (uint8_t)v;
             mx = max(mx, v);
         }
     }
