@@ -127,30 +127,31 @@ __device__ __forceinline__ uint8_t clahe_px(const ClaheGeom& g, const uint8_t* _
 }
 
 // ------------------------------------------------------------------------------------------------ median of 25
-// Forgetful selection: of 14 values neither the minimum nor the maximum can be the 13th of 25; drop both, take the next value in.
+// The classic 99-exchange selection network for the median of 25 (Devillard, "Fast median search", after Paeth); p[12] is the
+// median.  Its correctness for every input follows from the zero-one principle, checked exhaustively over all 2^25 binary inputs
+// (tools/check_median_network.py).  Exchanges whose outputs are never read again lose one half at compile time (174 live min / max).
 // values are two pixels packed as u16x2: VIMNMX.U16x2 orders both at once
 #define IT_CE(a, b) { const uint32_t _lo = __vminu2(a, b); b = __vmaxu2(a, b); a = _lo; }
-template <int N> __device__ __forceinline__ void ends_minmax(uint32_t (&v)[14]) {      // min -> v[0], max -> v[N-1]
-#pragma unroll
-    for (int i = 0; i < N / 2; i++) IT_CE(v[i], v[N - 1 - i]);
-#pragma unroll
-    for (int i = 1; i < (N + 1) / 2; i++) IT_CE(v[0], v[i]);
-#pragma unroll
-    for (int i = N / 2; i < N - 1; i++) IT_CE(v[i], v[N - 1]);
+__device__ __forceinline__ uint32_t median25(uint32_t (&p)[25]) {
+    IT_CE(p[0], p[1]) IT_CE(p[3], p[4]) IT_CE(p[2], p[4]) IT_CE(p[2], p[3]) IT_CE(p[6], p[7]) IT_CE(p[5], p[7])
+    IT_CE(p[5], p[6]) IT_CE(p[9], p[10]) IT_CE(p[8], p[10]) IT_CE(p[8], p[9]) IT_CE(p[12], p[13]) IT_CE(p[11], p[13])
+    IT_CE(p[11], p[12]) IT_CE(p[15], p[16]) IT_CE(p[14], p[16]) IT_CE(p[14], p[15]) IT_CE(p[18], p[19]) IT_CE(p[17], p[19])
+    IT_CE(p[17], p[18]) IT_CE(p[21], p[22]) IT_CE(p[20], p[22]) IT_CE(p[20], p[21]) IT_CE(p[23], p[24]) IT_CE(p[2], p[5])
+    IT_CE(p[3], p[6]) IT_CE(p[0], p[6]) IT_CE(p[0], p[3]) IT_CE(p[4], p[7]) IT_CE(p[1], p[7]) IT_CE(p[1], p[4])
+    IT_CE(p[11], p[14]) IT_CE(p[8], p[14]) IT_CE(p[8], p[11]) IT_CE(p[12], p[15]) IT_CE(p[9], p[15]) IT_CE(p[9], p[12])
+    IT_CE(p[13], p[16]) IT_CE(p[10], p[16]) IT_CE(p[10], p[13]) IT_CE(p[20], p[23]) IT_CE(p[17], p[23]) IT_CE(p[17], p[20])
+    IT_CE(p[21], p[24]) IT_CE(p[18], p[24]) IT_CE(p[18], p[21]) IT_CE(p[19], p[22]) IT_CE(p[8], p[17]) IT_CE(p[9], p[18])
+    IT_CE(p[0], p[18]) IT_CE(p[0], p[9]) IT_CE(p[10], p[19]) IT_CE(p[1], p[19]) IT_CE(p[1], p[10]) IT_CE(p[11], p[20])
+    IT_CE(p[2], p[20]) IT_CE(p[2], p[11]) IT_CE(p[12], p[21]) IT_CE(p[3], p[21]) IT_CE(p[3], p[12]) IT_CE(p[13], p[22])
+    IT_CE(p[4], p[22]) IT_CE(p[4], p[13]) IT_CE(p[14], p[23]) IT_CE(p[5], p[23]) IT_CE(p[5], p[14]) IT_CE(p[15], p[24])
+    IT_CE(p[6], p[24]) IT_CE(p[6], p[15]) IT_CE(p[7], p[16]) IT_CE(p[7], p[19]) IT_CE(p[13], p[21]) IT_CE(p[15], p[23])
+    IT_CE(p[7], p[13]) IT_CE(p[7], p[15]) IT_CE(p[1], p[9]) IT_CE(p[3], p[11]) IT_CE(p[5], p[17]) IT_CE(p[11], p[17])
+    IT_CE(p[9], p[17]) IT_CE(p[4], p[10]) IT_CE(p[6], p[12]) IT_CE(p[7], p[14]) IT_CE(p[4], p[6]) IT_CE(p[4], p[7])
+    IT_CE(p[12], p[14]) IT_CE(p[10], p[14]) IT_CE(p[6], p[7]) IT_CE(p[10], p[12]) IT_CE(p[6], p[10]) IT_CE(p[6], p[17])
+    IT_CE(p[12], p[17]) IT_CE(p[7], p[17]) IT_CE(p[7], p[10]) IT_CE(p[12], p[18]) IT_CE(p[7], p[12]) IT_CE(p[10], p[18])
+    IT_CE(p[12], p[20]) IT_CE(p[10], p[20]) IT_CE(p[10], p[12])
+    return p[12];
 }
-template <int N> struct Forget {
-    static __device__ __forceinline__ uint32_t run(uint32_t (&v)[14], const uint32_t (&rest)[11]) {
-        ends_minmax<N>(v);
-        v[0] = rest[14 - N];                       // the maximum at v[N-1] falls off the end, the minimum is overwritten
-        return Forget<N - 1>::run(v, rest);
-    }
-};
-template <> struct Forget<3> {
-    static __device__ __forceinline__ uint32_t run(uint32_t (&v)[14], const uint32_t (&)[11]) {
-        IT_CE(v[0], v[1]); IT_CE(v[1], v[2]); IT_CE(v[0], v[1]);
-        return v[1];
-    }
-};
 
 // ------------------------------------------------------------------------------------------------ CLAHE -> ... -> Canny map
 constexpr int CT_H = 64, CT_W = 64;                                   // output tile; region = tile + 6 halo on each side
@@ -220,14 +221,13 @@ clahe_canny_kernel(const uint8_t* __restrict__ gray, const uint8_t* __restrict__
         const int v = i / MPAIRS + 4, u = (i % MPAIRS) * 2 + 4;
         const int ym = clampi(y0 + v, H) - y0;                                    // value Sobel's replicate border sees
         const int xa = clampi(x0 + u, W) - x0, xb = clampi(x0 + u + 1, W) - x0;
-        uint32_t w14[14], rest[11];
+        uint32_t win[25];
 #pragma unroll
         for (int k = 0; k < 25; k++) {
             const uint8_t* r = s_g + (ym + k / 5 - 2) * RC_W + k % 5 - 2;
-            const uint32_t px = (uint32_t)r[xa] | ((uint32_t)r[xb] << 16);
-            if (k < 14) w14[k] = px; else rest[k - 14] = px;
+            win[k] = (uint32_t)r[xa] | ((uint32_t)r[xb] << 16);
         }
-        const uint32_t med = Forget<14>::run(w14, rest);
+        const uint32_t med = median25(win);
         s_m[v * RC_W + u] = (uint8_t)(med & 0xffu);
         s_m[v * RC_W + u + 1] = (uint8_t)(med >> 16);
     }

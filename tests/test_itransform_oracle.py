@@ -74,3 +74,10 @@ def test_stages_bit_exact_against_the_libraries():
     # addWeighted over all 65,536 byte pairs (the fused multiply-add decides 128 of them)
     a, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
     assert np.array_equal(O.add_weighted(a, b), cv2.addWeighted(a, 0.7, b, 0.3, 0))
+
+
+def test_median_network_of_the_cuda_kernel_is_a_median():
+    """Zero-one principle over all 2^25 binary inputs for the 99-exchange network compiled into csrc/kpd_itransform.cu."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_median_network.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
