@@ -178,14 +178,15 @@ __global__ void __launch_bounds__(PF_THREADS, (R * NT <= 24) ? 3 : 2) pw_ffma_ke
 }
 
 // Pixel-per-thread variant for the layers whose GEMM is too shallow for the tiled kernel above (K <= 96 with N <= 24: the
-// projections of features.1 / features.3; 49 -> 35 us and 56 -> 50 us at B = 256): the tiled kernel spends more
+// projections of features.1 / features.3, 49 -> 35 us and 56 -> 50 us at B = 256; and the K = 24 lateral as 4 warps = 4 channel
+// chunks per 32 pixels, 95-103 -> 87 us): the tiled kernel spends more
 // issue slots on its per-item prologue / epilogue than on 6..22 k-steps, and its lane-per-row float4 stores are 32 half-empty
 // sector writes per instruction.  Here a thread owns NPT output channels of one pixel (N / NPT threads per pixel), the weights sit in
 // shared memory (one broadcast LDS.128 per 4 FMAs), the pixel's K inputs come as float4 through L1, and the warp's outputs --
 // contiguous in memory -- leave through a padded shared-memory transposition as full 512-byte rows.  Accumulation order
 // (bias first, k ascending, SE factor applied to the input) is that of the tiled kernel: the results are bit-identical.
 template <int NPT>
-__global__ void __launch_bounds__(256) pw_px_kernel(const PwMma p) {
+__global__ void __launch_bounds__(256, NPT == 32 ? 3 : 2) pw_px_kernel(const PwMma p) {
     extern __shared__ __align__(16) float px_smem[];           // W [K][N / NPT][NPT + 4] | staging [8 warps][32][NPT + 4]
     constexpr int LDS_ = NPT + 4;                              // padded chunk / row pitch: the N / NPT chunk addresses of one LDS.128 fall into different banks
     const int K = p.K, N = p.N, tpp = N / NPT;
@@ -196,14 +197,13 @@ __global__ void __launch_bounds__(256) pw_px_kernel(const PwMma p) {
         *reinterpret_cast<float4*>(Ws + (k * tpp + ch) * LDS_ + q * 4) = __ldg(reinterpret_cast<const float4*>(p.Wraw) + i);
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t total = p.M * tpp;                            // one thread per (pixel, channel chunk)
-    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + (threadIdx.x & ~31));
-    if (warp0 >= total) return;
-    const int64_t gt = warp0 + lane;
-    const bool live = gt < total;
-    const int64_t m = live ? gt / tpp : p.M - 1;
-    const int ch = live ? (int)(gt - m * tpp) : 0, n0 = ch * NPT;
+    // a warp = 32 consecutive pixels x ONE channel chunk (all lanes read the same weights: full-warp broadcasts; four distinct
+    // chunk addresses per LDS.128 cost four shared-memory wavefronts each and made the K = 24 lateral LSU-bound at 114 us)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ch = warp % tpp, n0 = ch * NPT;
+    const int64_t m0 = ((int64_t)blockIdx.x * (8 / tpp) + warp / tpp) * 32;       // first pixel of this warp
+    if (m0 >= p.M) return;
+    const int64_t m = m0 + lane < p.M ? m0 + lane : p.M - 1;
     float acc[NPT];
 #pragma unroll
     for (int c4 = 0; c4 < NPT / 4; c4++) {
@@ -245,20 +245,20 @@ __global__ void __launch_bounds__(256) pw_px_kernel(const PwMma p) {
         *reinterpret_cast<float4*>(stg + lane * LDS_ + c4 * 4) = v;
     }
     __syncwarp();
-    // the warp's 32 x NPT outputs are one contiguous run of `out`: store it in memory order, 512 bytes per instruction
-    float4* op = reinterpret_cast<float4*>(p.out) + warp0 * (NPT / 4);
-    const int64_t lim = (total - warp0 < 32 ? total - warp0 : 32) * (NPT / 4);
+    // store in memory order: (NPT / 4) lanes cover one pixel's chunk (64 .. 128 contiguous bytes), full sectors per instruction
+    const int npix = (int)(p.M - m0 < 32 ? p.M - m0 : 32);
 #pragma unroll
     for (int j = 0; j < NPT / 4; j++) {
         const int e = j * 32 + lane, src_lane = e / (NPT / 4), q = e - src_lane * (NPT / 4);
-        if (e < lim) op[e] = *reinterpret_cast<const float4*>(stg + src_lane * LDS_ + q * 4);
+        if (src_lane < npix)
+            *reinterpret_cast<float4*>(p.out + (size_t)(m0 + src_lane) * N + n0 + q * 4) = *reinterpret_cast<const float4*>(stg + src_lane * LDS_ + q * 4);
     }
 }
 
 static int px_npt(const PwMma& p) {             // channels per thread of the pixel-per-thread kernel, 0 = not eligible
     if (p.out2 || (p.K & 3) || p.K > 96) return 0;
     if (p.N == 16 || p.N == 24) return p.N;
-    // (N = 128 as 4 threads x 32 channels per pixel -- the K = 24 lateral -- measured 114 us against 95-103 us for the tiled kernel: not taken)
+    if (p.N == 128 && p.K <= 32) return 32;            // the K = 24 lateral: 4 warps (channel chunks) per 32 pixels
     return 0;
 }
 
@@ -291,9 +291,10 @@ int pointwise_ffma(const PwMma& p, int sm_count, cudaStream_t s) {
     if (p.M <= 0) return 0;
     if (p.M >= ((int64_t)1 << 31) - PF_BM) { set_error("pointwise_ffma: M = %lld pixels exceeds the 32-bit pixel index", (long long)p.M); return KPD_ERR_UNSUPPORTED; }
     if (const int npt = px_npt(p)) {
-        const int64_t threads = p.M * (p.N / npt);
-        const size_t smem = sizeof(float) * ((size_t)p.K * (p.N / npt) * (npt + 4) + 8 * 32 * (npt + 4));
-        const int grid = (int)((threads + 255) / 256);
+        const int tpp = p.N / npt;                                // warps (channel chunks) per group of 32 pixels: 1 or 4
+        const size_t smem = sizeof(float) * ((size_t)p.K * tpp * (npt + 4) + 8 * 32 * (npt + 4));
+        const int64_t groups = (p.M + 31) / 32;                   // 8 / tpp pixel groups per CTA
+        const int grid = (int)((groups + (8 / tpp) - 1) / (8 / tpp));
         constexpr int PX_SMEM_MAX = 96 * 1024;          // the attribute is set once per device: K <= 96, N <= 128 always fit
         static uint64_t px_attr[3] = {};
         if (npt == 16) { KPD_CUDA(ensure_smem_attr(pw_px_kernel<16>, PX_SMEM_MAX, px_attr[0])); pw_px_kernel<16><<<grid, 256, smem, s>>>(p); }
