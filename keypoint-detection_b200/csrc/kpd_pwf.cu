@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(PF_THREADS, (R * NT <= 24) ? 3 : 2) pw_ffma_ke
 // contiguous in memory -- leave through a padded shared-memory transposition as full 512-byte rows.  Accumulation order
 // (bias first, k ascending, SE factor applied to the input) is that of the tiled kernel: the results are bit-identical.
 template <int NPT>
-__global__ void __launch_bounds__(256, NPT == 32 ? 3 : 2) pw_px_kernel(const PwMma p) {
+__global__ void __launch_bounds__(256, NPT == 32 ? 3 : 0) pw_px_kernel(const PwMma p) {
     extern __shared__ __align__(16) float px_smem[];           // W [K][N / NPT][NPT + 4] | staging [8 warps][32][NPT + 4]
     constexpr int LDS_ = NPT + 4;                              // padded chunk / row pitch: the N / NPT chunk addresses of one LDS.128 fall into different banks
     const int K = p.K, N = p.N, tpp = N / NPT;
