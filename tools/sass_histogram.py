@@ -25,7 +25,7 @@ for k in hist: tot.update({o: c for o, c in hist[k].items() if o in SPECIAL})
 print("# library totals:", ", ".join(f"{o} {c}" for o, c in sorted(tot.items(), key=lambda x: -x[1])))
 for k in sorted(hist, key=lambda k: -sum(hist[k].values())):
     h = hist[k]
-    name = re.sub(r"\(.*", "", demangle(k))[:90]
+    name = re.sub(r"\(.*", "", demangle(k).replace("(anonymous namespace)::", ""))[:90]
     sp = ", ".join(f"{o} {h[o]}" for o in SPECIAL if h.get(o))
     rest = ", ".join(f"{o} {c}" for o, c in h.most_common(40) if o not in SPECIAL)[:160]
     print(f"{name}\n    total {sum(h.values())} | {sp or '-'}\n    {rest}")
