@@ -187,6 +187,7 @@ size_t kpd_detect_scratch_bytes(int batch, int top_m);
  * grayscale == 0 (transforms.py:80-109): per-channel CLAHE -> GaussianBlur 3x3 s0.5 -> resize -> ImageNet mean/std;
  *   d_out float32 [batch,3,out_size,out_size].
  * d_scratch: kpd_itransform_scratch_bytes(...) bytes, 256-byte aligned; no allocation and no host synchronisation inside.
+ * Limits per call: images 16..16384 pixels per side, batch x planes <= 65535, batch x planes x height x width < 2^31.
  * kpd_itransform_stage_offsets: byte offsets of the stage planes inside the scratch buffer (tests / visualisation):
  *   [0] gray or colour planes u8 [B,planes,H,W], [1] CLAHE LUTs u8 [B,planes,tiles,256], [2] CLAHE (rgb: blurred) planes,
  *   [3] Canny map after hysteresis u8 (2 = edge), [4] blurred edge plane before the rescale, [5] horizontal-pass rows [B,planes,H,S]. */

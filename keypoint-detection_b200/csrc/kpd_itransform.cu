@@ -618,6 +618,8 @@ extern "C" int kpd_itransform(const uint8_t* d_src, int batch, int height, int w
     KPD_CHECK_ARG(out_size >= 1 && out_size <= 4096, "kpd_itransform: output size %d out of range", out_size);
     const int planes = grayscale ? 1 : 3, ntile = tiles_x * tiles_y, S = out_size, H = height, W = width;
     KPD_CHECK_ARG(batch * planes <= 65535, "kpd_itransform: batch x planes exceeds 65535");
+    KPD_CHECK_ARG((int64_t)batch * planes * H * W < ((int64_t)1 << 31) && (int64_t)batch * planes * ntile < ((int64_t)1 << 30),
+                  "kpd_itransform: %d x %dx%d pixels per call exceed the 2^31 limit of the tile indices (split the batch)", batch, H, W);
     const ITLayout L = it_layout(batch, H, W, planes, ntile, S);
     char* ws = (char*)d_scratch;
     ITParams p{};
