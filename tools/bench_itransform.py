@@ -29,8 +29,16 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=64)
     a = ap.parse_args()
     from dll.data import ITransform
-    from oracle.itransform import synth_photo
     B, H, W = a.batch, a.height, a.width
+    def synth_photo(h, w, seed):                 # smooth illumination + hard-edged shapes + sensor noise
+        rng = np.random.default_rng(seed)
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+        img = np.stack([120 + 70 * np.sin(xx / (19.0 + 3 * c) + seed) * np.cos(yy / (27.0 - 2 * c)) for c in range(3)], axis=-1)
+        for k in range(6):
+            cy, cx, ry, rx = rng.uniform(0, h), rng.uniform(0, w), rng.uniform(h / 12, h / 4), rng.uniform(w / 12, w / 4)
+            img[(np.abs(yy - cy) < ry) & (np.abs(xx - cx) < rx)] += rng.uniform(-80, 80, 3)
+        return np.clip(img + rng.normal(0, 5, img.shape), 0, 255).astype(np.uint8)
+
     uniq = [synth_photo(H, W, 500 + i) for i in range(16)]
     host = torch.from_numpy(np.stack([uniq[i % 16] for i in range(B)])).pin_memory()
     dev = host.cuda()
