@@ -471,7 +471,9 @@ def sub_itransform(lib, args, pk, steps):
                     "note": "pinned host batch copied in 4 chunks on a side stream under the previous chunk's kernels; PCIe-bound (0.92 MB of uint8 per image)"},
             "bit_exact_vs_host_libraries": exact, "kernels_ms": kern, "algorithmic_bytes": algo,
             "roofline": {"bound": "hbm", "achieved": algo / ms / 1e6, "peak": pk["hbm"], "unit": "GB/s", "frac": algo / ms / 1e6 / pk["hbm"],
-                         "note": "whole pipeline against its layer-boundary bytes (RGB in, float out); the stencil stages are issue-bound byte work"},
+                         "note": "whole pipeline against its layer-boundary bytes (RGB in, float out): the HBM fraction is not the binding limit here -- "
+                                 "the stencil stages are integer-ALU issue-bound (ncu, profiles/r02_itransform_ncu_full.csv: clahe_canny_kernel 3.0 of 4 "
+                                 "instructions per cycle per SM, ALU pipe 74 % busy, DRAM traffic = its algorithmic bytes)"},
             "cpu_baseline": {"value": cpu_ips, "unit": "images/sec", "cores": os.cpu_count(), "kind": "reference",
                              "sample": f"{n_cpu} images through the reference's own pipeline (cv2 {__import__('cv2').__version__} + Pillow), one image at a time"},
             "clocks": clocks}
