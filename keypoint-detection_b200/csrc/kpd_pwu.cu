@@ -30,7 +30,12 @@ struct PwUParams {
 };
 
 #define PU_TRACE(role, ev) do { if (p.trace && blockIdx.x == 0 && (ev) < 128) p.trace[(role) * 128 + (ev)] = clock64(); } while (0)
-constexpr int PU_EPI_WARPS = 8, PU_THREADS = 192 + 32 * PU_EPI_WARPS, PU_RS = 36, PU_MAXN = 640;
+#ifndef KPD_PU_SPLIT_WARPS
+#define KPD_PU_SPLIT_WARPS 8
+#endif
+constexpr int PU_SPLIT_WARPS = KPD_PU_SPLIT_WARPS, PU_SPLIT_THREADS = 32 * PU_SPLIT_WARPS, PU_EPI0 = 2 + PU_SPLIT_WARPS;   // warps: TMA, MMA, split, epilogue
+static_assert(PU_SPLIT_WARPS == 4 || PU_SPLIT_WARPS == 8, "split warps: 4 or 8 (the epilogue warps must start at a multiple of 4 + 2)");
+constexpr int PU_EPI_WARPS = 8, PU_THREADS = 64 + PU_SPLIT_THREADS + 32 * PU_EPI_WARPS, PU_RS = 36, PU_MAXN = 640;
 constexpr int PU_SC_FLOATS = 4 * 576;                         // SE factors staged per tile: (images a 128-row tile can span) x K floats
 constexpr int PU_A = 16384;                                   // one 128 x 32-float slab
 
@@ -67,7 +72,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), 4); mbar_init(free_bar(s), 1); }
+        for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), PU_SPLIT_WARPS); mbar_init(free_bar(s), 1); }
         for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PU_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -129,8 +134,9 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp < 6) {                              // ---------------- split warps 2..5: raw fp32 slab -> tf32 hi / lo slabs
-        const int t = (warp - 2) * 32 + lane;           // 0..127; float4 f = t + 128 i lives in row f >> 3 at chunk position f & 7
+    } else if (warp < PU_EPI0) {                        // ---------------- split warps: raw fp32 slab -> tf32 hi / lo slabs
+        const int t = (warp - 2) * 32 + lane;           // float4 f = t + PU_SPLIT_THREADS * i lives in row f >> 3 at chunk position f & 7
+        constexpr int NI = 1024 / PU_SPLIT_THREADS;      // float4 per thread per slab
         int stage = 0; uint32_t phase = 0; int tr2 = 0;
         for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
             const int tm = item / p.nchunks;
@@ -142,20 +148,20 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.se_scale) {
                 const uint32_t img0 = m0 / (uint32_t)p.hw, img1 = min(m0 + 127u, p.M - 1) / (uint32_t)p.hw;
                 const int nv = (int)(img1 - img0 + 1) * (p.K >> 2);
-                asm volatile("bar.sync 2, 128;" ::: "memory");                   // every split thread is done with the previous item's factors
+                asm volatile("bar.sync 2, %0;" ::"n"(PU_SPLIT_THREADS) : "memory");   // every split thread is done with the previous item's factors
                 const float4* src = reinterpret_cast<const float4*>(p.se_scale + (size_t)img0 * p.K);
-                for (int i = t; i < nv; i += 128) reinterpret_cast<float4*>(sscale)[i] = __ldg(src + i);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
+                for (int i = t; i < nv; i += PU_SPLIT_THREADS) reinterpret_cast<float4*>(sscale)[i] = __ldg(src + i);
+                asm volatile("bar.sync 2, %0;" ::"n"(PU_SPLIT_THREADS) : "memory");
 #pragma unroll
-                for (int i = 0; i < 8; i++) srow[i] = sscale + (size_t)(min(m0 + (uint32_t)((t >> 3) + 16 * i), p.M - 1) / (uint32_t)p.hw - img0) * p.K;
+                for (int i = 0; i < NI; i++) srow[i] = sscale + (size_t)(min(m0 + (uint32_t)((t >> 3) + (PU_SPLIT_THREADS / 8) * i), p.M - 1) / (uint32_t)p.hw - img0) * p.K;
             }
             for (int sl = 0; sl < nslabs; sl++) {
                 mbar_wait(full_bar(stage), phase);
                 if (t == 0) PU_TRACE(2, tr2++);
                 uint8_t* sp = smem + (size_t)stage * p.stage_bytes;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int f = t + 128 * i;                                   // float4 index: row f >> 3, stored chunk position f & 7
+                for (int i = 0; i < NI; i++) {
+                    const int f = t + PU_SPLIT_THREADS * i;                      // float4 index: row f >> 3, stored chunk position f & 7
                     float4 a = *reinterpret_cast<const float4*>(sp + f * 16);
                     if (p.se_scale) {
                         const int row = f >> 3, k = sl * 32 + (((f & 7) ^ (row & 7)) << 2);      // 128-byte swizzle: chunk position -> k
@@ -178,11 +184,11 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
-    } else {                                            // ---------------- epilogue warps 6..13: two per TMEM lane group, alternating 32-column chunks
+    } else {                                            // ---------------- epilogue warps: two per TMEM lane group, alternating 32-column chunks
         const int lg = warp & 3;                        // TMEM lane group this warp may access
-        const int cpar = (warp - 6) >> 2;               // chunk parity this warp drains
+        const int cpar = (warp - PU_EPI0) >> 2;         // chunk parity this warp drains
         const int rr4 = lane >> 3, q = lane & 7;
-        float* rt = red + (warp - 6) * (32 * PU_RS);
+        float* rt = red + (warp - PU_EPI0) * (32 * PU_RS);
         int acc = 0; uint32_t acc_phase = 0; int tr3 = 0;
         for (int item = blockIdx.x; item < p.total; item += gridDim.x) {
             const int tm = item / p.nchunks, n0 = (item - tm * p.nchunks) * p.Nc;
@@ -199,9 +205,9 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     roff[it] = ((size_t)(b * (p.H / p.up) + yy / p.up) * (p.W / p.up) + xx / p.up) * p.N;
                 }
             }
-            if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
+            if (warp == PU_EPI0 && lane == 0) PU_TRACE(3, tr3++);
             mbar_wait_warp(tfull_bar(acc), acc_phase, lane);
-            if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
+            if (warp == PU_EPI0 && lane == 0) PU_TRACE(3, tr3++);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * p.Nc);
             auto drain = [&](auto actfn) {
@@ -209,7 +215,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r[32];
                     tc_ld32(taddr + c0, r);
                     tc_wait_ld();
-                    if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
+                    if (warp == PU_EPI0 && lane == 0) PU_TRACE(3, tr3++);
                     const float* bp = sbias + n0 + c0;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -220,7 +226,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         *reinterpret_cast<float4*>(rt + lane * PU_RS + 4 * j) = pu_act4(v, actfn);
                     }
                     __syncwarp();
-                    if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
+                    if (warp == PU_EPI0 && lane == 0) PU_TRACE(3, tr3++);
                     // transposed read: lane = (row rr4 of 4, 4 channels q): one warp store covers four 128-byte row segments
                     const int n = n0 + c0 + 4 * q;
                     if (n < p.N && c0 + 4 * q < p.Nc) {                      // columns past the chunk belong to another item
@@ -255,7 +261,7 @@ pw_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
-            if (warp == 6 && lane == 0) PU_TRACE(3, tr3++);
+            if (warp == PU_EPI0 && lane == 0) PU_TRACE(3, tr3++);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
